@@ -1,0 +1,817 @@
+// api.cu -- the extern "C" boundary of libbbg.so (declared in include/bbg.h).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <string>
+
+#include "../../include/bbg.h"
+#include "ctx.cuh"
+#include "g1.cuh"
+#include "internal.hpp"
+
+namespace bbg {
+
+// ---- error text + context
+static thread_local std::string g_last_error;
+static std::string g_last_error_global;
+void set_last_error(const std::string& s)
+{
+    g_last_error = s;
+    g_last_error_global = s;
+}
+
+static Context* g_ctx = nullptr;
+static std::mutex g_ctx_mu;
+
+static int create_context(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_last_error("no CUDA device available (libbbg has no CPU fallback)");
+        return BBG_ERR_NO_DEVICE;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) {
+            device = 0;
+        }
+    }
+    if (device >= count) {
+        set_last_error("bbg_init: device index out of range");
+        return BBG_ERR_ARG;
+    }
+    BBG_CUDA(cudaSetDevice(device));
+    Context* c = new Context();
+    c->device = device;
+    cudaDeviceProp prop;
+    BBG_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    BBG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    BBG_CUDA(cudaEventCreate(&c->ev_a));
+    BBG_CUDA(cudaEventCreate(&c->ev_b));
+    g_ctx = c;
+    return BBG_OK;
+}
+
+int get_context(Context** out)
+{
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (g_ctx == nullptr) {
+        int rc = create_context(-1);
+        if (rc) return rc;
+    }
+    // callers may come from any thread: bind the device for this thread
+    BBG_CUDA(cudaSetDevice(g_ctx->device));
+    *out = g_ctx;
+    return BBG_OK;
+}
+
+// RAII device timer around the kernels of one host-pointer call
+struct DeviceTimer {
+    Context* c;
+    explicit DeviceTimer(Context* ctx) : c(ctx) { cudaEventRecord(c->ev_a, c->stream); }
+    int finish()
+    {
+        BBG_CUDA(cudaEventRecord(c->ev_b, c->stream));
+        BBG_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        BBG_CUDA(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+        c->last_kernel_ms = ms;
+        return BBG_OK;
+    }
+};
+
+// ---- Pippenger object: the SRS resident in HBM as n contiguous affine points
+struct PippengerObj {
+    affine_t* d_points = nullptr;
+    size_t n = 0;
+    const void* host_table = nullptr; // adopted 2n host table (for pointer recognition), may be null
+};
+static std::vector<PippengerObj*> g_pippengers;
+
+static int upload_even_entries(Context* ctx, const void* table2n, size_t n, affine_t* d_points)
+{
+    // strided copy: every other 64-byte entry
+    BBG_CUDA(cudaMemcpy2DAsync(d_points, 64, table2n, 128, 64, n, cudaMemcpyHostToDevice, ctx->stream));
+    return BBG_OK;
+}
+
+static const uint64_t G1_ONE_X[4] = { 0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL };
+static const uint64_t G1_ONE_Y[4] = { 0xa6ba871b8b1e1b3aULL, 0x14f1d651eb8e167bULL, 0xccdd46def0f28c58ULL, 0x1c14ef83340fbe5eULL };
+
+// monomials[0] = generator (1, 2); the file points follow (bb/srs/io.cpp:134-139, pippenger.cpp:7-16)
+static int decode_raw_points(Context* ctx, const uint8_t* raw, size_t num_file_points, affine_t* d_points_after_generator)
+{
+    if (num_file_points == 0) {
+        return BBG_OK;
+    }
+    int rc = ctx->msm_points.reserve(num_file_points * 64);
+    if (rc) return rc;
+    BBG_CUDA(cudaMemcpyAsync(ctx->msm_points.p, raw, num_file_points * 64, cudaMemcpyHostToDevice, ctx->stream));
+    return srs_decode_device(ctx, ctx->msm_points.p, num_file_points, d_points_after_generator, ctx->stream);
+}
+
+static int set_generator(Context* ctx, affine_t* d_point0)
+{
+    uint64_t g[8];
+    memcpy(g, G1_ONE_X, 32);
+    memcpy(g + 4, G1_ONE_Y, 32);
+    BBG_CUDA(cudaMemcpyAsync(d_point0, g, 64, cudaMemcpyHostToDevice, ctx->stream));
+    BBG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BBG_OK;
+}
+
+static uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+// Reads up to `degree - 1` file points from <dir>/transcript00.dat, transcript01.dat, ... into a host buffer
+// (raw, undecoded).  Manifest = 7 big-endian u32 (bb/srs/io.cpp:11-45); field 4 = num_g1_points.
+static int read_transcript_raw(const char* dir, size_t degree, std::vector<uint8_t>& raw)
+{
+    raw.clear();
+    size_t need = degree > 0 ? degree - 1 : 0;
+    raw.reserve(need * 64);
+    for (int num = 0; raw.size() / 64 < need; ++num) {
+        char path[4096];
+        snprintf(path, sizeof(path), "%s/transcript%02d.dat", dir, num);
+        std::ifstream f(path, std::ifstream::binary);
+        if (!f.good()) {
+            break;
+        }
+        uint8_t man[28];
+        f.read((char*)man, 28);
+        if (f.gcount() != 28) {
+            break;
+        }
+        size_t num_g1 = be32(man + 16);
+        size_t to_read = std::min(num_g1, need - raw.size() / 64);
+        size_t old = raw.size();
+        raw.resize(old + to_read * 64);
+        f.read((char*)raw.data() + old, (std::streamsize)(to_read * 64));
+        if ((size_t)f.gcount() != to_read * 64) {
+            raw.resize(old + (size_t)f.gcount() / 64 * 64);
+            break;
+        }
+    }
+    if (raw.size() / 64 < need) {
+        // same condition and wording as bb/srs/io.cpp:159-161
+        set_last_error("Only read " + std::to_string(raw.size() / 64 + 1) + " points but require " + std::to_string(degree) +
+                       ". Is your srs large enough?");
+        return BBG_ERR_SRS;
+    }
+    return BBG_OK;
+}
+
+static PippengerObj* new_obj(Context* ctx, size_t n)
+{
+    PippengerObj* o = new PippengerObj();
+    o->n = n;
+    if (cudaMalloc(&o->d_points, std::max<size_t>(n, 1) * 64) != cudaSuccess) {
+        set_last_error("cudaMalloc failed for SRS points");
+        delete o;
+        return nullptr;
+    }
+    (void)ctx;
+    g_pippengers.push_back(o);
+    return o;
+}
+
+// probe kernels ------------------------------------------------------------------------------------
+template <class F> __global__ void k_field_op(int op, const Fe<F>* a, const Fe<F>* b, Fe<F>* out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fe<F> x = fe_load<F>(a + i);
+    Fe<F> y = b ? fe_load<F>(b + i) : fe_zero<F>();
+    Fe<F> r;
+    switch (op) {
+    case 0: r = fe_mul(x, y); break;
+    case 1: r = fe_add(x, y); break;
+    case 2: r = fe_sub(x, y); break;
+    case 3: r = fe_sqr(x); break;
+    case 4: r = fe_to_mont(fe_reduce_once(x)); break;
+    case 5: r = fe_from_mont(x); break;
+    case 7: r = fe_reduce_once(x); break;
+    case 8: r = fe_neg(x); break;
+    default: r = fe_zero<F>();
+    }
+    fe_store(out + i, r);
+}
+__global__ void k_g1_op(int op, const jac_t* a, const void* b, jac_t* out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    jac_t ja;
+    ja.x = fe_load<FqParams>(&a[i].x);
+    ja.y = fe_load<FqParams>(&a[i].y);
+    ja.z = fe_load<FqParams>(&a[i].z);
+    xyzz_t p = xyzz_from_jacobian(ja);
+    if (op == 0) {
+        affine_t q = affine_load(reinterpret_cast<const affine_t*>(b) + i);
+        if (!affine_is_inf(q)) {
+            xyzz_madd(p, q);
+        }
+    } else if (op == 1) {
+        const jac_t* bj = reinterpret_cast<const jac_t*>(b) + i;
+        jac_t jb;
+        jb.x = fe_load<FqParams>(&bj->x);
+        jb.y = fe_load<FqParams>(&bj->y);
+        jb.z = fe_load<FqParams>(&bj->z);
+        xyzz_t q = xyzz_from_jacobian(jb);
+        xyzz_add(p, q);
+    } else {
+        p = xyzz_dbl(p);
+    }
+    jac_t r = xyzz_to_jacobian(p);
+    fe_store(&out[i].x, r.x);
+    fe_store(&out[i].y, r.y);
+    fe_store(&out[i].z, r.z);
+}
+
+// NTT kind -> prologue/epilogue scalings (bb/polynomials/polynomial_arithmetic.cpp:374-484)
+static hf::Fr coset_generator()
+{
+    return hf::from_u64(5); // fr::coset_generator(0), bb/ecc/curves/bn254/fr.hpp:44-59
+}
+static int ntt_kind_params(int kind, unsigned log_n, size_t generator_size, const void* constant, bool& inverse, NttScale& pro, NttScale& epi)
+{
+    const uint64_t n = 1ull << log_n;
+    if (generator_size == 0 || generator_size > n) {
+        generator_size = n; // evaluation_domain.cpp:64
+    }
+    hf::Fr k = hf::one();
+    if (kind >= 4 && kind <= 7) {
+        if (constant == nullptr) {
+            set_last_error("ntt: this kind needs a constant");
+            return BBG_ERR_ARG;
+        }
+        k = hf::reduce(hf::load(constant));
+    }
+    const hf::Fr g = coset_generator();
+    const hf::Fr n_inv = hf::invert(hf::from_u64(n));
+    inverse = false;
+    pro = NttScale();
+    epi = NttScale();
+    switch (kind) {
+    case BBG_FFT: break;
+    case BBG_IFFT:
+        inverse = true;
+        epi.present = true;
+        epi.start = n_inv;
+        break;
+    case BBG_COSET_FFT:
+        pro.present = true;
+        pro.start = hf::one();
+        pro.has_shift = true;
+        pro.shift = g;
+        pro.size = generator_size;
+        break;
+    case BBG_COSET_IFFT:
+        inverse = true;
+        epi.present = true;
+        epi.start = n_inv;
+        epi.has_shift = true;
+        epi.shift = hf::invert(g);
+        break;
+    case BBG_FFT_WITH_CONSTANT:
+        epi.present = true;
+        epi.start = k;
+        break;
+    case BBG_IFFT_WITH_CONSTANT:
+        inverse = true;
+        epi.present = true;
+        epi.start = hf::mul(n_inv, k);
+        break;
+    case BBG_COSET_FFT_WITH_CONSTANT:
+        pro.present = true;
+        pro.start = k;
+        pro.has_shift = true;
+        pro.shift = g;
+        pro.size = generator_size;
+        break;
+    case BBG_COSET_FFT_WITH_GENERATOR_SHIFT:
+        pro.present = true;
+        pro.start = hf::one();
+        pro.has_shift = true;
+        pro.shift = hf::mul(g, k);
+        pro.size = generator_size;
+        break;
+    default:
+        set_last_error("ntt: unknown kind");
+        return BBG_ERR_ARG;
+    }
+    return BBG_OK;
+}
+
+static int log2_exact(size_t n, unsigned& lg)
+{
+    lg = 0;
+    while (((size_t)1 << lg) < n) ++lg;
+    if (((size_t)1 << lg) != n || n == 0) {
+        set_last_error("ntt: size must be a power of two");
+        return BBG_ERR_ARG;
+    }
+    return BBG_OK;
+}
+
+struct DomainObj {
+    size_t n;
+};
+
+} // namespace bbg
+
+using namespace bbg;
+
+#define GET_CTX()                     \
+    Context* ctx = nullptr;           \
+    {                                 \
+        int _rc = get_context(&ctx);  \
+        if (_rc) return _rc;          \
+    }                                 \
+    std::lock_guard<std::mutex> _lk(ctx->mu)
+
+extern "C" {
+
+int bbg_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (g_ctx != nullptr) {
+        return BBG_OK;
+    }
+    return create_context(device);
+}
+
+void bbg_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (g_ctx == nullptr) return;
+    cudaSetDevice(g_ctx->device);
+    cudaDeviceSynchronize();
+    for (auto* o : g_pippengers) {
+        cudaFree(o->d_points);
+        delete o;
+    }
+    g_pippengers.clear();
+    for (auto& kv : g_ctx->ntt_twiddles) cudaFree(kv.second);
+    for (int d = 0; d < 2; ++d) {
+        if (g_ctx->ntt_stage_tw[d]) cudaFree(g_ctx->ntt_stage_tw[d]);
+    }
+    DevBuf* bufs[] = { &g_ctx->msm_scalars, &g_ctx->msm_counts, &g_ctx->msm_offsets, &g_ctx->msm_cursors, &g_ctx->msm_sorted,
+                       &g_ctx->msm_buckets, &g_ctx->msm_partials, &g_ctx->msm_reduce, &g_ctx->msm_scan_tmp, &g_ctx->msm_result,
+                       &g_ctx->msm_points, &g_ctx->ntt_data, &g_ctx->ntt_scratch, &g_ctx->ntt_pro, &g_ctx->ntt_epi, &g_ctx->ntt_small };
+    for (auto* b : bufs) b->release();
+    cudaEventDestroy(g_ctx->ev_a);
+    cudaEventDestroy(g_ctx->ev_b);
+    cudaStreamDestroy(g_ctx->stream);
+    delete g_ctx;
+    g_ctx = nullptr;
+}
+
+const char* bbg_last_error(void) { return g_last_error.empty() ? g_last_error_global.c_str() : g_last_error.c_str(); }
+
+int bbg_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+uint64_t bbg_kernel_launches(void) { return g_ctx ? g_ctx->launches : 0; }
+double bbg_last_device_ms(void) { return g_ctx ? g_ctx->last_kernel_ms : 0.0; }
+
+void* bbg_malloc(size_t size)
+{
+    Context* ctx = nullptr;
+    if (get_context(&ctx)) return nullptr;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, size ? size : 1, cudaHostAllocDefault) != cudaSuccess) {
+        set_last_error("cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+void bbg_free(void* ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
+// ---- Pippenger objects
+static void* finish_obj(Context* ctx, PippengerObj* o, int rc)
+{
+    if (rc == BBG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        set_last_error("stream sync failed while building the SRS");
+        rc = BBG_ERR_CUDA;
+    }
+    if (rc != BBG_OK) {
+        bbg_delete_pippenger(o);
+        return nullptr;
+    }
+    return o;
+}
+
+void* bbg_new_pippenger(const uint8_t* points, size_t num_points)
+{
+    Context* ctx = nullptr;
+    if (get_context(&ctx)) return nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PippengerObj* o = new_obj(ctx, num_points);
+    if (!o) return nullptr;
+    int rc = BBG_OK;
+    if (num_points > 0) {
+        rc = set_generator(ctx, o->d_points);
+        if (!rc) rc = decode_raw_points(ctx, points, num_points - 1, o->d_points + 1);
+    }
+    return finish_obj(ctx, o, rc);
+}
+
+void* bbg_new_pippenger_from_path(const char* srs_dir, size_t num_points)
+{
+    Context* ctx = nullptr;
+    if (get_context(&ctx)) return nullptr;
+    std::vector<uint8_t> raw;
+    if (read_transcript_raw(srs_dir, num_points, raw)) return nullptr;
+    return bbg_new_pippenger(raw.data(), num_points);
+}
+
+void* bbg_new_pippenger_from_table(const void* table2n, size_t num_points)
+{
+    Context* ctx = nullptr;
+    if (get_context(&ctx)) return nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PippengerObj* o = new_obj(ctx, num_points);
+    if (!o) return nullptr;
+    o->host_table = table2n;
+    int rc = num_points ? upload_even_entries(ctx, table2n, num_points, o->d_points) : BBG_OK;
+    return finish_obj(ctx, o, rc);
+}
+
+void* bbg_new_pippenger_from_points(const void* points, size_t num_points)
+{
+    Context* ctx = nullptr;
+    if (get_context(&ctx)) return nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PippengerObj* o = new_obj(ctx, num_points);
+    if (!o) return nullptr;
+    int rc = BBG_OK;
+    if (num_points && cudaMemcpyAsync(o->d_points, points, num_points * 64, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        set_last_error("H2D copy of points failed");
+        rc = BBG_ERR_CUDA;
+    }
+    return finish_obj(ctx, o, rc);
+}
+
+void bbg_delete_pippenger(void* pippenger)
+{
+    PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
+    if (!o) return;
+    auto it = std::find(g_pippengers.begin(), g_pippengers.end(), o);
+    if (it != g_pippengers.end()) g_pippengers.erase(it);
+    if (o->d_points) cudaFree(o->d_points);
+    delete o;
+}
+
+size_t bbg_pippenger_num_points(void* pippenger) { return pippenger ? reinterpret_cast<PippengerObj*>(pippenger)->n : 0; }
+const void* bbg_pippenger_device_points(void* pippenger) { return pippenger ? reinterpret_cast<PippengerObj*>(pippenger)->d_points : nullptr; }
+
+int bbg_pippenger_get_point_table(void* pippenger, void* table2n_out)
+{
+    GET_CTX();
+    PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
+    if (!o || !table2n_out) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    if (o->n == 0) return BBG_OK;
+    void* d_table = nullptr;
+    BBG_CUDA(cudaMalloc(&d_table, o->n * 128));
+    int rc = point_table_device(ctx, o->d_points, o->n, d_table, ctx->stream);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(table2n_out, d_table, o->n * 128, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            set_last_error(cudaGetErrorString(e));
+            rc = BBG_ERR_CUDA;
+        }
+    }
+    cudaFree(d_table);
+    return rc;
+}
+
+static int msm_host_scalars(Context* ctx, const void* scalars, size_t n, const affine_t* d_points, size_t stride, void* result)
+{
+    int rc;
+    if ((rc = ctx->msm_scalars.reserve(std::max<size_t>(n, 1) * 32))) return rc;
+    if ((rc = ctx->msm_result.reserve(96))) return rc;
+    if (n) BBG_CUDA(cudaMemcpyAsync(ctx->msm_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    DeviceTimer tm(ctx);
+    if ((rc = msm_device(ctx, ctx->msm_scalars.p, n, d_points, stride, ctx->msm_result.p, ctx->stream))) return rc;
+    BBG_CUDA(cudaMemcpyAsync(result, ctx->msm_result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    return tm.finish();
+}
+
+int bbg_pippenger_unsafe(void* pippenger, const void* scalars, size_t from, size_t range, void* result)
+{
+    GET_CTX();
+    PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
+    if (!o || !result || (range && !scalars)) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    if (from + range > o->n) {
+        set_last_error("pippenger_unsafe: [from, from+range) exceeds the SRS");
+        return BBG_ERR_SRS;
+    }
+    return msm_host_scalars(ctx, scalars, range, o->d_points + from, 1, result);
+}
+
+int bbg_pippenger_unsafe_dev(void* pippenger, const void* d_scalars, size_t from, size_t range, void* d_result, void* stream)
+{
+    GET_CTX();
+    PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
+    if (!o || !d_result) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    if (from + range > o->n) {
+        set_last_error("pippenger_unsafe: [from, from+range) exceeds the SRS");
+        return BBG_ERR_SRS;
+    }
+    return msm_device(ctx, d_scalars, range, o->d_points + from, 1, d_result, (cudaStream_t)stream);
+}
+
+int bbg_pippenger(const void* scalars, const void* points_table2n, size_t num_points, int handle_edge_cases, void* result)
+{
+    (void)handle_edge_cases; // the device path always handles doubling / infinity
+    GET_CTX();
+    if (!result || (num_points && (!scalars || !points_table2n))) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    // resident copy?  (points may be monomials + 2*from, bb/.../pippenger.cpp:27-31)
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(points_table2n);
+    for (auto* o : g_pippengers) {
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(o->host_table);
+        if (base && p >= base && p < base + o->n * 128 && (size_t)(p - base) % 128 == 0) {
+            size_t from = (size_t)(p - base) / 128;
+            if (from + num_points <= o->n) {
+                return msm_host_scalars(ctx, scalars, num_points, o->d_points + from, 1, result);
+            }
+        }
+    }
+    int rc;
+    if ((rc = ctx->msm_points.reserve(std::max<size_t>(num_points, 1) * 64))) return rc;
+    if (num_points && (rc = upload_even_entries(ctx, points_table2n, num_points, (affine_t*)ctx->msm_points.p))) return rc;
+    return msm_host_scalars(ctx, scalars, num_points, (const affine_t*)ctx->msm_points.p, 1, result);
+}
+
+int bbg_msm_points(const void* scalars, const void* points, size_t num_points, void* result)
+{
+    GET_CTX();
+    if (!result || (num_points && (!scalars || !points))) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    int rc;
+    if ((rc = ctx->msm_points.reserve(std::max<size_t>(num_points, 1) * 64))) return rc;
+    if (num_points) BBG_CUDA(cudaMemcpyAsync(ctx->msm_points.p, points, num_points * 64, cudaMemcpyHostToDevice, ctx->stream));
+    return msm_host_scalars(ctx, scalars, num_points, (const affine_t*)ctx->msm_points.p, 1, result);
+}
+
+int bbg_msm_points_dev(const void* d_scalars, const void* d_points, size_t point_stride, size_t num_points, void* d_result, void* stream)
+{
+    GET_CTX();
+    return msm_device(ctx, d_scalars, num_points, d_points, point_stride ? point_stride : 1, d_result, (cudaStream_t)stream);
+}
+
+int bbg_generate_pippenger_point_table(const void* points, void* table, size_t num_points)
+{
+    GET_CTX();
+    if (num_points == 0) return BBG_OK;
+    void *d_pts = nullptr, *d_table = nullptr;
+    BBG_CUDA(cudaMalloc(&d_pts, num_points * 64));
+    cudaError_t e = cudaMalloc(&d_table, num_points * 128);
+    if (e != cudaSuccess) {
+        cudaFree(d_pts);
+        set_last_error(cudaGetErrorString(e));
+        return BBG_ERR_CUDA;
+    }
+    int rc = BBG_OK;
+    e = cudaMemcpyAsync(d_pts, points, num_points * 64, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = point_table_device(ctx, d_pts, num_points, d_table, ctx->stream);
+    if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(table, d_table, num_points * 128, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_pts);
+    cudaFree(d_table);
+    if (e != cudaSuccess) {
+        set_last_error(cudaGetErrorString(e));
+        return BBG_ERR_CUDA;
+    }
+    return rc;
+}
+
+int bbg_g1_sum(const void* elements, size_t num_points, void* result)
+{
+    GET_CTX();
+    int rc;
+    if ((rc = ctx->msm_points.reserve(std::max<size_t>(num_points, 1) * 96))) return rc;
+    if ((rc = ctx->msm_result.reserve(96))) return rc;
+    if (num_points) BBG_CUDA(cudaMemcpyAsync(ctx->msm_points.p, elements, num_points * 96, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = g1_sum_device(ctx, ctx->msm_points.p, num_points, ctx->msm_result.p, ctx->stream))) return rc;
+    BBG_CUDA(cudaMemcpyAsync(result, ctx->msm_result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    BBG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BBG_OK;
+}
+int bbg_g1_sum_dev(const void* d_elements, size_t num_points, void* d_result, void* stream)
+{
+    GET_CTX();
+    return g1_sum_device(ctx, d_elements, num_points, d_result, (cudaStream_t)stream);
+}
+
+int bbg_read_g1_elements_from_buffer(void* elements, const char* buffer, size_t buffer_size)
+{
+    GET_CTX();
+    size_t n = buffer_size / 64;
+    if (n == 0) return BBG_OK;
+    void* d_out = nullptr;
+    BBG_CUDA(cudaMalloc(&d_out, n * 64));
+    int rc = decode_raw_points(ctx, reinterpret_cast<const uint8_t*>(buffer), n, (affine_t*)d_out);
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMemcpyAsync(elements, d_out, n * 64, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) {
+        set_last_error(cudaGetErrorString(e));
+        return BBG_ERR_CUDA;
+    }
+    return rc;
+}
+
+int bbg_read_transcript_g1(void* monomials, size_t degree, const char* srs_dir)
+{
+    if (degree == 0) return BBG_OK;
+    std::vector<uint8_t> raw;
+    int rc = read_transcript_raw(srs_dir, degree, raw);
+    if (rc) return rc;
+    memcpy(monomials, G1_ONE_X, 32);
+    memcpy(reinterpret_cast<uint8_t*>(monomials) + 32, G1_ONE_Y, 32);
+    return bbg_read_g1_elements_from_buffer(reinterpret_cast<uint8_t*>(monomials) + 64, (const char*)raw.data(), raw.size());
+}
+
+// ---- NTT
+int bbg_ntt_dev(void* d_coeffs, size_t n, int kind, size_t generator_size, const void* constant, void* stream)
+{
+    GET_CTX();
+    unsigned lg;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    bool inverse;
+    NttScale pro, epi;
+    if ((rc = ntt_kind_params(kind, lg, generator_size, constant, inverse, pro, epi))) return rc;
+    return ntt_device(ctx, d_coeffs, d_coeffs, lg, inverse, pro, epi, 0, 0, (cudaStream_t)stream);
+}
+
+int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant)
+{
+    GET_CTX();
+    unsigned lg;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    bool inverse;
+    NttScale pro, epi;
+    if ((rc = ntt_kind_params(kind, lg, generator_size, constant, inverse, pro, epi))) return rc;
+    if ((rc = ctx->ntt_data.reserve(n * 32))) return rc;
+    BBG_CUDA(cudaMemcpyAsync(ctx->ntt_data.p, coeffs, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    DeviceTimer tm(ctx);
+    if ((rc = ntt_device(ctx, ctx->ntt_data.p, ctx->ntt_data.p, lg, inverse, pro, epi, 0, 0, ctx->stream))) return rc;
+    BBG_CUDA(cudaMemcpyAsync(coeffs, ctx->ntt_data.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    return tm.finish();
+}
+
+static int coset_fft_ext_device(Context* ctx, void* d_coeffs, unsigned lg, size_t ext, cudaStream_t st)
+{
+    unsigned lg_ext = 0;
+    while (((size_t)1 << lg_ext) < ext) ++lg_ext;
+    if (((size_t)1 << lg_ext) != ext || lg + lg_ext > 28) {
+        set_last_error("coset_fft: domain_extension must be a power of two with n*ext <= 2^28");
+        return BBG_ERR_ARG;
+    }
+    const size_t n = (size_t)1 << lg;
+    int rc;
+    // the interleaved output overwrites the input, so keep a copy of the n input coefficients
+    if ((rc = ctx->ntt_small.reserve(n * 32))) return rc;
+    BBG_CUDA(cudaMemcpyAsync(ctx->ntt_small.p, d_coeffs, n * 32, cudaMemcpyDeviceToDevice, st));
+    // coset k uses generator g * w_{ext n}^k (polynomial_arithmetic.cpp:414-421)
+    const hf::Fr prim = ntt_root_of_unity(lg + lg_ext);
+    hf::Fr gk = coset_generator();
+    for (size_t k = 0; k < ext; ++k) {
+        NttScale pro, epi;
+        pro.present = true;
+        pro.start = hf::one();
+        pro.has_shift = true;
+        pro.shift = gk;
+        pro.size = n;
+        if ((rc = ntt_device(ctx, ctx->ntt_small.p, d_coeffs, lg, false, pro, epi, lg_ext, (unsigned)k, st))) return rc;
+        gk = hf::mul(gk, prim);
+    }
+    return BBG_OK;
+}
+
+int bbg_coset_fft_ext_dev(void* d_coeffs, size_t n, size_t domain_extension, void* stream)
+{
+    GET_CTX();
+    unsigned lg;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    return coset_fft_ext_device(ctx, d_coeffs, lg, domain_extension, (cudaStream_t)stream);
+}
+
+int bbg_coset_fft_ext(void* coeffs, size_t n, size_t domain_extension)
+{
+    GET_CTX();
+    unsigned lg;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    if ((rc = ctx->ntt_data.reserve(n * domain_extension * 32))) return rc;
+    BBG_CUDA(cudaMemcpyAsync(ctx->ntt_data.p, coeffs, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    DeviceTimer tm(ctx);
+    if ((rc = coset_fft_ext_device(ctx, ctx->ntt_data.p, lg, domain_extension, ctx->stream))) return rc;
+    BBG_CUDA(cudaMemcpyAsync(coeffs, ctx->ntt_data.p, n * domain_extension * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    return tm.finish();
+}
+
+void* bbg_new_evaluation_domain(size_t circuit_size)
+{
+    DomainObj* d = new DomainObj();
+    d->n = circuit_size;
+    return d;
+}
+void bbg_delete_evaluation_domain(void* domain) { delete reinterpret_cast<DomainObj*>(domain); }
+int bbg_ifft(void* coeffs, void* domain) { return bbg_ntt(coeffs, reinterpret_cast<DomainObj*>(domain)->n, BBG_IFFT, 0, nullptr); }
+int bbg_coset_fft_with_generator_shift(void* coeffs, const void* constant, void* domain)
+{
+    return bbg_ntt(coeffs, reinterpret_cast<DomainObj*>(domain)->n, BBG_COSET_FFT_WITH_GENERATOR_SHIFT, 0, constant);
+}
+
+int bbg_domain_constants(size_t n, void* out6)
+{
+    unsigned lg;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    hf::Fr c[6];
+    c[0] = hf::reduce(ntt_root_of_unity(lg));
+    c[1] = hf::invert(c[0]);
+    c[2] = hf::from_u64(n);
+    c[3] = hf::invert(c[2]);
+    c[4] = coset_generator();
+    c[5] = hf::invert(c[4]);
+    memcpy(out6, c, sizeof(c));
+    return BBG_OK;
+}
+
+// ---- probes
+int bbg_field_op(int field, int op, const void* a, const void* b, void* out, size_t n)
+{
+    GET_CTX();
+    if (n == 0) return BBG_OK;
+    void *da = nullptr, *db = nullptr, *dout = nullptr;
+    BBG_CUDA(cudaMalloc(&da, n * 32));
+    BBG_CUDA(cudaMalloc(&dout, n * 32));
+    if (b) BBG_CUDA(cudaMalloc(&db, n * 32));
+    BBG_CUDA(cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) BBG_CUDA(cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (field == 0) {
+        k_field_op<FqParams><<<div_up(n, 128), 128, 0, ctx->stream>>>(op, (const fq_t*)da, (const fq_t*)db, (fq_t*)dout, n);
+    } else {
+        k_field_op<FrParams><<<div_up(n, 128), 128, 0, ctx->stream>>>(op, (const fr_t*)da, (const fr_t*)db, (fr_t*)dout, n);
+    }
+    ctx->launches += 1;
+    BBG_CUDA(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    BBG_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(da);
+    cudaFree(dout);
+    if (db) cudaFree(db);
+    return BBG_OK;
+}
+
+int bbg_g1_op(int op, const void* a, const void* b, void* out, size_t n)
+{
+    GET_CTX();
+    if (n == 0) return BBG_OK;
+    const size_t bsz = op == 0 ? 64 : 96;
+    void *da = nullptr, *db = nullptr, *dout = nullptr;
+    BBG_CUDA(cudaMalloc(&da, n * 96));
+    BBG_CUDA(cudaMalloc(&dout, n * 96));
+    if (b) BBG_CUDA(cudaMalloc(&db, n * bsz));
+    BBG_CUDA(cudaMemcpyAsync(da, a, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) BBG_CUDA(cudaMemcpyAsync(db, b, n * bsz, cudaMemcpyHostToDevice, ctx->stream));
+    k_g1_op<<<div_up(n, 64), 64, 0, ctx->stream>>>(op, (const jac_t*)da, db, (jac_t*)dout, n);
+    ctx->launches += 1;
+    BBG_CUDA(cudaMemcpyAsync(out, dout, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    BBG_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(da);
+    cudaFree(dout);
+    if (db) cudaFree(db);
+    return BBG_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,27 @@
+// internal.hpp -- declarations shared by api.cu, msm.cu and ntt.cu (not part of the C-ABI).
+#pragma once
+#include "ctx.cuh"
+#include "host_field.hpp"
+
+namespace bbg {
+
+// msm.cu
+int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_points, size_t point_stride, void* d_out, cudaStream_t st);
+int g1_sum_device(Context* ctx, const void* d_jacs, size_t n, void* d_out, cudaStream_t st);
+int srs_decode_device(Context* ctx, const void* d_raw, size_t n, void* d_points, cudaStream_t st);
+int point_table_device(Context* ctx, const void* d_points, size_t n, void* d_table, cudaStream_t st);
+int compact_even_device(Context* ctx, const void* d_table, size_t n, void* d_points, cudaStream_t st);
+
+// ntt.cu
+struct NttScale {
+    bool present = false;
+    hf::Fr start;       // constant factor
+    bool has_shift = false;
+    hf::Fr shift;       // geometric factor shift^i
+    uint64_t size = 0;  // prologue only: applies to i < size
+};
+int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, bool inverse, const NttScale& pro, const NttScale& epi,
+               unsigned out_shift, unsigned out_off, cudaStream_t st);
+hf::Fr ntt_root_of_unity(unsigned log_n);
+
+} // namespace bbg

@@ -1,0 +1,593 @@
+// ntt.cu -- radix-2 NTT / iNTT / coset-FFT over BN254 fr for sm_100a.
+//
+// Replaces barretenberg's polynomial_arithmetic::{fft, ifft, coset_fft, coset_ifft, *_with_constant,
+// coset_fft_with_generator_shift} (bb/polynomials/polynomial_arithmetic.cpp:374-484).  The reference
+// runs log2(n) radix-2 DIT passes over the whole array with per-round twiddle tables
+// (fft_inner_parallel :140-255).  Here the transform is factored N = N_1 * ... * N_P (P = 2..4,
+// N_p <= 256) in the four-step / Cooley-Tukey sense, one kernel launch per factor:
+//
+//   pass p:  for every fixed (o_1..o_{p-1}, i_{p+1}..i_P): an N_p-point DIF NTT over digit i_p held in
+//            registers (radix-8 butterflies, 8 elements per thread) with shared-memory exchanges between
+//            radix-8 rounds, then the inter-pass twiddle w_N^(N_1..N_{p-1} * o_p * rest) fused into the
+//            store.  A CTA tile is N_p rows x 8 adjacent columns, so every global access is a 256-byte
+//            contiguous run of 32-byte field elements (128-bit loads/stores).
+//   last  :  reads rows contiguously, writes the digit-reversed (= natural) index so the output is in
+//            natural order like the reference's, with the 1/n, constant and coset g^-i scalings fused.
+//   first :  the coset pre-scaling g^i (scale_by_generator :97-117, i < generator_size only) fused
+//            into the load.
+//
+// HBM traffic: P reads + P writes of the array (+ one 32-byte twiddle per element per inner pass);
+// arithmetic: (log2 N)/2 + P - 1 (+ scalings) Montgomery multiplies per element -- the kernel is
+// bound by the integer pipe (IMAD.WIDE), not by HBM; see DESIGN.md.
+#include "ctx.cuh"
+#include "field.cuh"
+#include "internal.hpp"
+
+namespace bbg {
+
+using fr = Fe<FrParams>;
+
+static constexpr int NTT_THREADS = 256;
+static constexpr int NTT_COLS = 8;                       // columns per tile
+static constexpr int NTT_TILE_ELEMS = NTT_THREADS * 8;   // 2048 elements per CTA
+static constexpr int NTT_PAD = 9;                        // row pitch in 16-byte units (8 columns + 1 pad)
+static constexpr int NTT_SMEM_BYTES = 2 * (NTT_TILE_ELEMS / NTT_COLS) * NTT_PAD * 16; // 73,728 B
+static constexpr int NTT_MAX_PASSES = 4;
+
+struct PassParams {
+    const fr* src;
+    fr* dst;
+    const fr* tw_big;   // w_N^e, e in [0, N)
+    const fr* stage_tw; // w_{2^g}^j (or inverse), j in [0, 2^(g-1))
+    uint32_t log_n;
+    uint32_t g;       // this pass transforms a digit of g bits
+    uint32_t below;   // bits below the digit
+    uint32_t above;   // bits above the digit
+    uint32_t last;
+    uint32_t inverse;
+    // last pass: where each higher digit lands in the natural-order output index
+    uint32_t g1;               // bits of the first digit (the tile's columns)
+    uint32_t num_mid;          // digits 2..P-1
+    uint32_t mid_bits[2], mid_src_shift[2], mid_dst_shift[2];
+    // fused pre-scaling (first pass): x[i] *= pro_hi[i >> split] * pro_lo[i & mask], i < pro_size
+    const fr* pro_lo;
+    const fr* pro_hi;
+    uint32_t pro_split;
+    uint64_t pro_size;
+    // fused post-scaling (last pass): mode 0 none, 1 constant, 2 epi_hi[o >> split] * epi_lo[o & mask]
+    uint32_t epi_mode;
+    const fr* epi_lo;
+    const fr* epi_hi;
+    uint32_t epi_split;
+    fr epi_const;
+    // output interleave for the extended coset FFT: natural index o lands at (o << out_shift) + out_off
+    uint32_t out_shift, out_off;
+};
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return __brev(x) >> (32 - bits); }
+
+__device__ __forceinline__ void smem_store(uint4* sm, uint32_t half_stride, uint32_t idx, const fr& v)
+{
+    sm[idx] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    sm[half_stride + idx] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ fr smem_load(const uint4* sm, uint32_t half_stride, uint32_t idx)
+{
+    uint4 a = sm[idx], b = sm[half_stride + idx];
+    fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+// DIF butterfly: (u, v) -> (u + v, (u - v) * w)
+__device__ __forceinline__ void bfly(fr& u, fr& v, const fr& w)
+{
+    fr s = fe_add(u, v);
+    fr d = fe_sub(u, v);
+    u = s;
+    v = fe_mul(d, w);
+}
+__device__ __forceinline__ void bfly_notw(fr& u, fr& v)
+{
+    fr s = fe_add(u, v);
+    v = fe_sub(u, v);
+    u = s;
+}
+
+// Three (or fewer) DIF stages on the 8 registers x[j], j = 3-bit value of row bits [w0, w0+3).
+// Stages run for row bits b_hi, b_hi-1, ..., w0 (b_hi <= w0 + 2). lo = row bits below w0.
+__device__ __forceinline__ void radix8_round(fr (&x)[8], uint32_t g, uint32_t w0, uint32_t b_hi, uint32_t lo, const fr* __restrict__ stage_tw)
+{
+    // In the last round (w0 == 0, hence lo == 0 for every thread) the exponent is zero exactly when
+    // j == 0: those butterflies skip the multiply.  The test is warp-uniform, so nothing diverges.
+    const bool tail = (w0 == 0);
+    if (b_hi >= w0 + 2) {
+        // bit w0+2: pairs (j, j+4); exponent ((j&3) << w0 | lo) << (g-1-(w0+2))
+        const uint32_t sh = g - 3 - w0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (tail && j == 0) {
+                bfly_notw(x[j], x[j + 4]);
+            } else {
+                const uint32_t e = (((uint32_t)j << w0) | lo) << sh;
+                fr w = fe_load_nc<FrParams>(stage_tw + e);
+                bfly(x[j], x[j + 4], w);
+            }
+        }
+    }
+    if (b_hi >= w0 + 1) {
+        const uint32_t sh = g - 2 - w0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (tail && j == 0) {
+                bfly_notw(x[j], x[j + 2]);
+                bfly_notw(x[j + 4], x[j + 6]);
+            } else {
+                const uint32_t e = (((uint32_t)j << w0) | lo) << sh;
+                fr w = fe_load_nc<FrParams>(stage_tw + e);
+                bfly(x[j], x[j + 2], w);
+                bfly(x[j + 4], x[j + 6], w);
+            }
+        }
+    }
+    {
+        if (tail) {
+            bfly_notw(x[0], x[1]);
+            bfly_notw(x[2], x[3]);
+            bfly_notw(x[4], x[5]);
+            bfly_notw(x[6], x[7]);
+        } else {
+            const uint32_t e = lo << (g - 1 - w0);
+            fr w = fe_load_nc<FrParams>(stage_tw + e);
+            bfly(x[0], x[1], w);
+            bfly(x[2], x[3], w);
+            bfly(x[4], x[5], w);
+            bfly(x[6], x[7], w);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
+{
+    extern __shared__ uint4 sm[];
+    const uint32_t half_stride = (NTT_TILE_ELEMS / NTT_COLS) * NTT_PAD;
+
+    const uint32_t g = P.g;
+    const uint32_t R = 1u << g;                   // rows per tile
+    const uint32_t tiles_per_cta = NTT_THREADS >> g; // R threads per tile (g <= 8)
+    const uint32_t tile_local = threadIdx.x >> g;
+    const uint32_t tau = threadIdx.x & (R - 1);
+    const uint32_t col = tau & 7;
+    const uint32_t q = tau >> 3;                  // [0, R/8)
+    const uint64_t N = 1ull << P.log_n;
+    const uint64_t num_tiles = N >> (g + 3);
+    const uint64_t tile = (uint64_t)blockIdx.x * tiles_per_cta + tile_local;
+    const bool active = tile < num_tiles;
+    const uint32_t sm_base = tile_local * R * NTT_PAD; // this tile's rows inside the CTA's shared memory
+    const uint32_t rows8 = R >> 3;
+
+    // ---- tile coordinates
+    uint64_t in_base = 0;     // address of (row 0, col 0)
+    uint64_t rest0 = 0;       // non-last: first value of the low index; last: first o_1 of the tile
+    uint64_t mid = 0;
+    if (!P.last) {
+        const uint64_t chunks = 1ull << (P.below - 3); // column chunks per hi value
+        const uint64_t hi = tile / chunks;
+        rest0 = (tile % chunks) << 3;
+        in_base = (hi << (g + P.below)) + rest0;
+    } else {
+        const uint64_t o1_chunks = 1ull << (P.g1 - 3);
+        rest0 = (tile % o1_chunks) << 3;
+        mid = tile / o1_chunks;
+    }
+
+    fr x[8];
+    // ---- load (round-0 register layout: rows j * R/8 + q, column col)
+    if (!P.last) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t row = (uint32_t)j * rows8 + q;
+                const uint64_t a = in_base + ((uint64_t)row << P.below) + col;
+                x[j] = fe_load<FrParams>(P.src + a);
+                if (P.pro_lo != nullptr && a < P.pro_size) {
+                    fr s = fe_mul(fe_load_nc<FrParams>(P.pro_hi + (a >> P.pro_split)),
+                                  fe_load_nc<FrParams>(P.pro_lo + (a & ((1ull << P.pro_split) - 1))));
+                    x[j] = fe_mul(x[j], s);
+                }
+            }
+        }
+    } else {
+        // rows are contiguous in memory: stage through shared memory with lanes along the rows
+        if (active) {
+            const uint32_t mid_bits_total = P.above - P.g1;
+#pragma unroll 1
+            for (uint32_t it = 0; it < 8; ++it) {
+                const uint32_t idx = it * R + tau;   // [0, 8R): column-major
+                const uint32_t c = idx >> g, row = idx & (R - 1);
+                const uint64_t a = ((((rest0 + c) << mid_bits_total) | mid) << g) + row;
+                fr v = fe_load<FrParams>(P.src + a);
+                smem_store(sm, half_stride, sm_base + row * NTT_PAD + c, v);
+            }
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t row = (uint32_t)j * rows8 + q;
+                x[j] = smem_load(sm, half_stride, sm_base + row * NTT_PAD + col);
+            }
+        }
+    }
+
+    // ---- radix-8 rounds over row bits g-1 .. 0
+    int b_hi = (int)g - 1;
+    uint32_t w0 = g - 3; // first round always has a full 3-bit window (g >= 3)
+    bool first = true;
+    while (true) {
+        if (!first) {
+            // exchange through shared memory: gather rows {hi_part, j, lo_part}
+            __syncthreads();
+            if (active) {
+                const uint32_t lo_part = q & ((1u << w0) - 1), hi_part = q >> w0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t row = (hi_part << (w0 + 3)) | ((uint32_t)j << w0) | lo_part;
+                    x[j] = smem_load(sm, half_stride, sm_base + row * NTT_PAD + col);
+                }
+            }
+        }
+        const uint32_t lo_part = q & ((1u << w0) - 1);
+        if (active) {
+            radix8_round(x, g, w0, (uint32_t)b_hi, lo_part, P.stage_tw);
+        }
+        b_hi = (int)w0 - 1;
+        if (b_hi < 0) {
+            break;
+        }
+        // write back for the next round (each thread overwrites exactly the rows it read: no hazard)
+        if (active) {
+            const uint32_t hi_part = q >> w0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t row = (hi_part << (w0 + 3)) | ((uint32_t)j << w0) | lo_part;
+                smem_store(sm, half_stride, sm_base + row * NTT_PAD + col, x[j]);
+            }
+        }
+        first = false;
+        w0 = b_hi >= 2 ? (uint32_t)b_hi - 2 : 0;
+    }
+
+    // ---- store.  After the last round (w0 == 0) thread holds rows (q << 3) | j; row rho holds X[bitrev_g(rho)].
+    if (!active) {
+        return;
+    }
+    if (!P.last) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t rho = (q << 3) | (uint32_t)j;
+            const uint32_t o = bitrev(rho, g);
+            const uint64_t rest = rest0 + col;
+            // inter-pass twiddle w_N^( 2^above * o * rest )
+            uint64_t e = (((uint64_t)o * rest) << P.above) & (N - 1);
+            if (e != 0) {
+                if (P.inverse) {
+                    e = N - e;
+                }
+                x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.tw_big + e));
+            }
+            const uint64_t a = in_base + ((uint64_t)o << P.below) + col;
+            fe_store(P.dst + a, x[j]);
+        }
+    } else {
+        // natural-order output index: o_1 + sum_q o_q * 2^(bits before q) + o_P * 2^above
+        uint64_t obase = rest0 + col;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            if ((uint32_t)d < P.num_mid) {
+                const uint64_t dig = (mid >> P.mid_src_shift[d]) & ((1ull << P.mid_bits[d]) - 1);
+                obase |= dig << P.mid_dst_shift[d];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t rho = (q << 3) | (uint32_t)j;
+            const uint64_t o = obase | ((uint64_t)bitrev(rho, g) << P.above);
+            if (P.epi_mode == 1) {
+                x[j] = fe_mul(x[j], P.epi_const);
+            } else if (P.epi_mode == 2) {
+                fr s = fe_mul(fe_load_nc<FrParams>(P.epi_hi + (o >> P.epi_split)),
+                              fe_load_nc<FrParams>(P.epi_lo + (o & ((1ull << P.epi_split) - 1))));
+                x[j] = fe_mul(x[j], s);
+            }
+            fe_store(P.dst + ((o << P.out_shift) + P.out_off), x[j]);
+        }
+    }
+}
+
+// ---- N <= 32: direct O(N^2) DFT by one warp (everything fused, nothing worth tiling)
+struct SmallParams {
+    const fr* src;
+    fr* dst;
+    uint32_t log_n;
+    uint32_t inverse;
+    fr root;        // w_N or its inverse
+    uint32_t has_pro;
+    fr pro_start, pro_shift;
+    uint64_t pro_size;
+    uint32_t epi_mode; // 0 none, 1 const, 2 const * shift^o
+    fr epi_const, epi_shift;
+    uint32_t out_shift, out_off;
+};
+__global__ void __launch_bounds__(32) k_ntt_small(const SmallParams P)
+{
+    __shared__ fr xs[32];
+    const uint32_t n = 1u << P.log_n;
+    const uint32_t o = threadIdx.x;
+    if (o < n) {
+        fr v = fe_load<FrParams>(P.src + o);
+        if (P.has_pro && o < P.pro_size) {
+            v = fe_mul(v, fe_mul(P.pro_start, fe_pow(P.pro_shift, o)));
+        }
+        xs[o] = v;
+    }
+    __syncthreads();
+    if (o >= n) {
+        return;
+    }
+    const fr wo = fe_pow(P.root, o); // w^o
+    fr acc = fe_zero<FrParams>();
+    // Horner over i: sum_i x_i (w^o)^i
+    for (int i = (int)n - 1; i >= 0; --i) {
+        acc = fe_add(fe_mul(acc, wo), xs[i]);
+    }
+    if (P.epi_mode == 1) {
+        acc = fe_mul(acc, P.epi_const);
+    } else if (P.epi_mode == 2) {
+        acc = fe_mul(acc, fe_mul(P.epi_const, fe_pow(P.epi_shift, o)));
+    }
+    fe_store(P.dst + (((uint64_t)o << P.out_shift) + P.out_off), acc);
+}
+
+// ---- table builders
+// out[e] = base^e * start, e in [0, count): each thread does one exponentiation + a short running product
+__global__ void __launch_bounds__(256) k_powers(fr* __restrict__ out, uint64_t count, fr base, fr start, uint32_t log_stride)
+{
+    // out[j] = start * base^(j << log_stride)
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t j0 = t * 8;
+    if (j0 >= count) {
+        return;
+    }
+    const fr step = fe_pow(base, 1ull << log_stride);
+    fr cur = fe_mul(start, fe_pow(base, j0 << log_stride));
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        if (j0 + j < count) {
+            fe_store(out + j0 + j, fe_reduce_once(cur));
+        }
+        cur = fe_mul(cur, step);
+    }
+}
+
+// fr: a primitive 2^28-th root of unity, Montgomery form (bb/ecc/curves/bn254/fr.hpp:27-30)
+static const uint64_t FR_ROOT_28[4] = { 0x636e735580d13d9cULL, 0xa22bf3742445ffd6ULL, 0x56452ac01eb203d8ULL,
+                                        0x1860ef942963f9e7ULL };
+
+static fr to_dev(const hf::Fr& a)
+{
+    fr r;
+    for (int i = 0; i < 4; ++i) {
+        r.l[2 * i] = (uint32_t)a.d[i];
+        r.l[2 * i + 1] = (uint32_t)(a.d[i] >> 32);
+    }
+    return r;
+}
+
+// get_root_of_unity(k): the 2^28-th root squared 28 - k times (bb/ecc/fields/field_impl.hpp:496-503)
+hf::Fr ntt_root_of_unity(unsigned log_n)
+{
+    hf::Fr r;
+    for (int i = 0; i < 4; ++i) r.d[i] = FR_ROOT_28[i];
+    for (unsigned i = 28; i > log_n; --i) {
+        r = hf::sqr(r);
+    }
+    return r;
+}
+
+static int launch_powers(Context* ctx, fr* out, uint64_t count, const hf::Fr& base, const hf::Fr& start, uint32_t log_stride, cudaStream_t st)
+{
+    const uint64_t threads = (count + 7) / 8;
+    k_powers<<<div_up(threads, 256), 256, 0, st>>>(out, count, to_dev(base), to_dev(start), log_stride);
+    ctx->launches += 1;
+    BBG_CUDA(cudaGetLastError());
+    return BBG_OK;
+}
+
+// stage twiddles: for g = 1..8, table_g[j] = w_{2^g}^j (dir 0) or w_{2^g}^-j (dir 1), j < 2^(g-1); offset(g) = 2^(g-1) - 1
+static int ensure_stage_tables(Context* ctx, cudaStream_t st)
+{
+    if (ctx->ntt_stage_tw[0] != nullptr) {
+        return BBG_OK;
+    }
+    for (int dir = 0; dir < 2; ++dir) {
+        fr* tab = nullptr;
+        BBG_CUDA(cudaMalloc(&tab, 256 * sizeof(fr)));
+        for (unsigned g = 1; g <= 8; ++g) {
+            hf::Fr w = ntt_root_of_unity(g);
+            if (dir) {
+                w = hf::invert(w);
+            }
+            int rc = launch_powers(ctx, tab + ((1u << (g - 1)) - 1), 1u << (g - 1), w, hf::one(), 0, st);
+            if (rc) return rc;
+        }
+        ctx->ntt_stage_tw[dir] = tab;
+    }
+    return BBG_OK;
+}
+
+static int ensure_big_table(Context* ctx, unsigned log_n, const fr** out, cudaStream_t st)
+{
+    auto it = ctx->ntt_twiddles.find(log_n);
+    if (it != ctx->ntt_twiddles.end()) {
+        *out = (const fr*)it->second;
+        return BBG_OK;
+    }
+    fr* tab = nullptr;
+    const uint64_t N = 1ull << log_n;
+    BBG_CUDA(cudaMalloc(&tab, N * sizeof(fr)));
+    int rc = launch_powers(ctx, tab, N, ntt_root_of_unity(log_n), hf::one(), 0, st);
+    if (rc) return rc;
+    ctx->ntt_twiddles[log_n] = tab;
+    *out = tab;
+    return BBG_OK;
+}
+
+// In-place (src == dst allowed) transform of 2^log_n elements on the device.
+//   pro : x[i] *= start * shift^i for i < size, before the transform
+//   epi : X[o] *= start (* shift^o), after the transform
+//   out index = (o << out_shift) + out_off inside dst
+int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, bool inverse, const NttScale& pro, const NttScale& epi,
+               unsigned out_shift, unsigned out_off, cudaStream_t st)
+{
+    if (log_n > 28) {
+        set_last_error("ntt: fr has 2-adicity 28, log2(n) must be <= 28");
+        return BBG_ERR_ARG;
+    }
+    const uint64_t N = 1ull << log_n;
+    hf::Fr root = ntt_root_of_unity(log_n);
+    if (inverse) {
+        root = hf::invert(root);
+    }
+    if (log_n <= 5) {
+        SmallParams sp;
+        sp.src = (const fr*)d_src;
+        sp.dst = (fr*)d_dst;
+        sp.log_n = log_n;
+        sp.inverse = inverse;
+        sp.root = to_dev(root);
+        sp.has_pro = pro.present;
+        sp.pro_start = to_dev(pro.present ? pro.start : hf::one());
+        sp.pro_shift = to_dev(pro.present && pro.has_shift ? pro.shift : hf::one());
+        sp.pro_size = pro.size;
+        sp.epi_mode = epi.present ? (epi.has_shift ? 2 : 1) : 0;
+        sp.epi_const = to_dev(epi.present ? epi.start : hf::one());
+        sp.epi_shift = to_dev(epi.present && epi.has_shift ? epi.shift : hf::one());
+        sp.out_shift = out_shift;
+        sp.out_off = out_off;
+        k_ntt_small<<<1, 32, 0, st>>>(sp);
+        ctx->launches += 1;
+        BBG_CUDA(cudaGetLastError());
+        return BBG_OK;
+    }
+
+    int rc;
+    if ((rc = ensure_stage_tables(ctx, st))) return rc;
+    const fr* tw_big = nullptr;
+    if ((rc = ensure_big_table(ctx, log_n, &tw_big, st))) return rc;
+    if ((rc = ctx->ntt_scratch.reserve(N * sizeof(fr)))) return rc;
+    fr* scratch = (fr*)ctx->ntt_scratch.p;
+
+    // factorisation: P passes of nearly equal size, each 3..8 bits
+    const unsigned num_passes = log_n <= 16 ? 2 : (log_n <= 24 ? 3 : 4);
+    unsigned gb[NTT_MAX_PASSES];
+    for (unsigned p = 0; p < num_passes; ++p) {
+        gb[p] = log_n / num_passes + (p < log_n % num_passes ? 1 : 0);
+    }
+
+    // two-level scaling tables (lo: shift^j, hi: start * shift^(j << split))
+    const uint32_t split = (log_n + 1) / 2;
+    const fr *pro_lo = nullptr, *pro_hi = nullptr, *epi_lo = nullptr, *epi_hi = nullptr;
+    const uint64_t lo_count = 1ull << split, hi_count = 1ull << (log_n - split);
+    if (pro.present) {
+        if ((rc = ctx->ntt_pro.reserve((lo_count + hi_count) * sizeof(fr)))) return rc;
+        fr* lo = (fr*)ctx->ntt_pro.p;
+        fr* hi = lo + lo_count;
+        const hf::Fr sh = pro.has_shift ? pro.shift : hf::one();
+        if ((rc = launch_powers(ctx, lo, lo_count, sh, hf::one(), 0, st))) return rc;
+        if ((rc = launch_powers(ctx, hi, hi_count, sh, pro.start, split, st))) return rc;
+        pro_lo = lo;
+        pro_hi = hi;
+    }
+    if (epi.present && epi.has_shift) {
+        if ((rc = ctx->ntt_epi.reserve((lo_count + hi_count) * sizeof(fr)))) return rc;
+        fr* lo = (fr*)ctx->ntt_epi.p;
+        fr* hi = lo + lo_count;
+        if ((rc = launch_powers(ctx, lo, lo_count, epi.shift, hf::one(), 0, st))) return rc;
+        if ((rc = launch_powers(ctx, hi, hi_count, epi.shift, epi.start, split, st))) return rc;
+        epi_lo = lo;
+        epi_hi = hi;
+    }
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
+        attr_set = true;
+    }
+
+    unsigned above = 0;
+    for (unsigned p = 0; p < num_passes; ++p) {
+        PassParams pp;
+        const bool last = (p == num_passes - 1);
+        pp.src = (p == 0) ? (const fr*)d_src : scratch;
+        pp.dst = last ? (fr*)d_dst : scratch;
+        pp.tw_big = tw_big;
+        pp.stage_tw = (const fr*)ctx->ntt_stage_tw[inverse ? 1 : 0] + ((1u << (gb[p] - 1)) - 1);
+        pp.log_n = log_n;
+        pp.g = gb[p];
+        pp.above = above;
+        pp.below = log_n - above - gb[p];
+        pp.last = last;
+        pp.inverse = inverse;
+        pp.g1 = gb[0];
+        pp.num_mid = 0;
+        for (int d = 0; d < 2; ++d) {
+            pp.mid_bits[d] = pp.mid_src_shift[d] = pp.mid_dst_shift[d] = 0;
+        }
+        if (last) {
+            // mid = (o_2, ..., o_{P-1}) with o_2 most significant
+            pp.num_mid = num_passes - 2;
+            unsigned dst_shift = gb[0];
+            unsigned remaining = above - gb[0];
+            for (unsigned d = 0; d < pp.num_mid; ++d) {
+                const unsigned bits = gb[1 + d];
+                remaining -= bits;
+                pp.mid_bits[d] = bits;
+                pp.mid_src_shift[d] = remaining;
+                pp.mid_dst_shift[d] = dst_shift;
+                dst_shift += bits;
+            }
+        }
+        pp.pro_lo = (p == 0) ? pro_lo : nullptr;
+        pp.pro_hi = (p == 0) ? pro_hi : nullptr;
+        pp.pro_split = split;
+        pp.pro_size = pro.present ? pro.size : 0;
+        pp.epi_mode = 0;
+        pp.epi_lo = pp.epi_hi = nullptr;
+        pp.epi_split = split;
+        pp.epi_const = to_dev(hf::one());
+        pp.out_shift = 0;
+        pp.out_off = 0;
+        if (last) {
+            if (epi.present) {
+                pp.epi_mode = epi.has_shift ? 2 : 1;
+                pp.epi_lo = epi_lo;
+                pp.epi_hi = epi_hi;
+                pp.epi_const = to_dev(epi.start);
+            }
+            pp.out_shift = out_shift;
+            pp.out_off = out_off;
+        }
+        const uint64_t num_tiles = N >> (gb[p] + 3);
+        const unsigned tiles_per_cta = NTT_THREADS >> gb[p];
+        const unsigned blocks = (unsigned)((num_tiles + tiles_per_cta - 1) / tiles_per_cta);
+        k_ntt_pass<<<blocks, NTT_THREADS, NTT_SMEM_BYTES, st>>>(pp);
+        ctx->launches += 1;
+        above += gb[p];
+    }
+    BBG_CUDA(cudaGetLastError());
+    return BBG_OK;
+}
+
+} // namespace bbg

@@ -1,0 +1,125 @@
+/* bbg.h -- C-ABI of libbbg.so: B200-native BN254 G1 MSM + fr NTT behind barretenberg's prover API.
+ *
+ * Plain C, plain pointers and sizes, int status codes (0 = ok; bbg_last_error() has the text).
+ * Every entry point names the barretenberg interface it replaces; "bb/" abbreviates
+ * barretenberg/src/aztec/ in AztecProtocol/aztec-2.0.  Data layouts are barretenberg's:
+ *   fr / fq            32 B, 4 x u64 little-endian limbs, Montgomery form (R = 2^256), any value in [0, 2p)
+ *   g1::affine_element 64 B {x, y}; point at infinity <=> bit 255 of x
+ *   g1::element        96 B {x, y, z} Jacobian; same infinity flag
+ * "host" pointers are ordinary (pageable or pinned) host memory; "_dev" variants take device
+ * pointers and a cudaStream_t (as void*) and never synchronise.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point returns BBG_ERR_NO_DEVICE.
+ */
+#ifndef BBG_H
+#define BBG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBG_OK 0
+#define BBG_ERR_CUDA 1
+#define BBG_ERR_ARG 2
+#define BBG_ERR_NO_DEVICE 3
+#define BBG_ERR_SRS 4
+#define BBG_ERR_IO 5
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int bbg_init(int device);              /* bind the process to a CUDA device (idempotent; -1 = current/0) */
+void bbg_shutdown(void);
+const char* bbg_last_error(void);
+int bbg_device_count(void);
+uint64_t bbg_kernel_launches(void);    /* kernels this library has launched so far (bench.py reports it) */
+double bbg_last_device_ms(void);       /* CUDA-event time of the kernels of the last host-pointer call */
+
+/* bb/ecc/curves/bn254/scalar_multiplication/c_bind.cpp:11-19  bbmalloc / bbfree.
+ * Returns page-locked host memory so the host-pointer entry points copy at full PCIe rate. */
+void* bbg_malloc(size_t size);
+void bbg_free(void* ptr);
+
+/* ---- SRS + Pippenger object ----------------------------------------------------------------- */
+/* bb/ecc/curves/bn254/scalar_multiplication/c_bind.cpp:21-29 new_pippenger(points, num_points):
+ * `points` = raw transcript bytes of num_points-1 G1 points (64 B each, bb/srs/io.cpp:47-67 format);
+ * monomial 0 is the generator.  Decoded (bswap + to-Montgomery) on the device. */
+void* bbg_new_pippenger(const uint8_t* points, size_t num_points);
+/* bb/.../pippenger.cpp:18-25 Pippenger(path, num_points): reads <dir>/transcriptNN.dat (bb/srs/io.cpp:134-162). */
+void* bbg_new_pippenger_from_path(const char* srs_dir, size_t num_points);
+/* Adopt a host table already in barretenberg's 2n-entry interleaved form [P0, phi(P0), P1, ...]
+ * (what ProverReferenceString::get_monomials() returns, bb/plonk/reference_string/reference_string.hpp:24-38).
+ * The host pointer is remembered so bbg_pippenger() can recognise it. */
+void* bbg_new_pippenger_from_table(const void* table2n, size_t num_points);
+/* Adopt a plain host array of num_points affine elements. */
+void* bbg_new_pippenger_from_points(const void* points, size_t num_points);
+/* c_bind.cpp:31-34 delete_pippenger */
+void bbg_delete_pippenger(void* pippenger);
+/* pippenger.hpp:47-49 get_num_points / get_point_table (copies the 2n interleaved table to host memory) */
+size_t bbg_pippenger_num_points(void* pippenger);
+int bbg_pippenger_get_point_table(void* pippenger, void* table2n_out);
+const void* bbg_pippenger_device_points(void* pippenger); /* n contiguous affine points in HBM */
+
+/* c_bind.cpp:36-43 pippenger_unsafe(pippenger, scalars, from, range, result) ==
+ * Pippenger::pippenger_unsafe(scalars, from, range) (pippenger.cpp:27-31): MSM over monomials [from, from+range).
+ * scalars: `range` fr elements; result: one g1::element (96 B). */
+int bbg_pippenger_unsafe(void* pippenger, const void* scalars, size_t from, size_t range, void* result);
+int bbg_pippenger_unsafe_dev(void* pippenger, const void* d_scalars, size_t from, size_t range, void* d_result, void* stream);
+
+/* bb/.../scalar_multiplication.hpp:139-148  pippenger(scalars, points, num_points, state, handle_edge_cases)
+ * and pippenger_unsafe(...).  `points` is the 2n interleaved table (even entries are read).  If it lies inside a
+ * table adopted with bbg_new_pippenger_from_table the resident device copy is used, otherwise the points
+ * are uploaded for this call.  The runtime state argument of the reference has no device counterpart.
+ * Both variants are safe for repeated points and points at infinity. */
+int bbg_pippenger(const void* scalars, const void* points_table2n, size_t num_points, int handle_edge_cases, void* result);
+/* same with a plain (stride-1) affine array */
+int bbg_msm_points(const void* scalars, const void* points, size_t num_points, void* result);
+int bbg_msm_points_dev(const void* d_scalars, const void* d_points, size_t point_stride, size_t num_points, void* d_result, void* stream);
+
+/* scalar_multiplication.hpp:94 generate_pippenger_point_table(points, table, num_points); table may alias points */
+int bbg_generate_pippenger_point_table(const void* points, void* table, size_t num_points);
+/* c_bind.cpp:45-51 g1_sum(points, num_points, result): sum of Jacobian elements (partial-MSM combiner) */
+int bbg_g1_sum(const void* elements, size_t num_points, void* result);
+int bbg_g1_sum_dev(const void* d_elements, size_t num_points, void* d_result, void* stream);
+
+/* bb/srs/io.hpp:10-18 */
+int bbg_read_transcript_g1(void* monomials, size_t degree, const char* srs_dir);
+int bbg_read_g1_elements_from_buffer(void* elements, const char* buffer, size_t buffer_size);
+
+/* ---- NTT family (bb/polynomials/polynomial_arithmetic.hpp:23-39), in place, natural order ---- */
+#define BBG_FFT 0                              /* fft(coeffs, domain)                          */
+#define BBG_IFFT 1                             /* ifft                                         */
+#define BBG_COSET_FFT 2                        /* coset_fft(coeffs, domain)                    */
+#define BBG_COSET_IFFT 3                       /* coset_ifft                                   */
+#define BBG_FFT_WITH_CONSTANT 4                /* fft_with_constant(coeffs, domain, value)     */
+#define BBG_IFFT_WITH_CONSTANT 5               /* ifft_with_constant                           */
+#define BBG_COSET_FFT_WITH_CONSTANT 6          /* coset_fft_with_constant                      */
+#define BBG_COSET_FFT_WITH_GENERATOR_SHIFT 7   /* coset_fft_with_generator_shift               */
+/* n = domain.size (power of two, <= 2^28); generator_size = domain.generator_size (0 = n);
+ * constant: one fr (Montgomery) for kinds 4..7, ignored otherwise. */
+int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant);
+int bbg_ntt_dev(void* d_coeffs, size_t n, int kind, size_t generator_size, const void* constant, void* stream);
+/* coset_fft(coeffs, small_domain, large_domain, domain_extension) (polynomial_arithmetic.cpp:401-456):
+ * coeffs holds ext*n elements, the first n are the input; output interleaved out[ext*i + k]. */
+int bbg_coset_fft_ext(void* coeffs, size_t n, size_t domain_extension);
+int bbg_coset_fft_ext_dev(void* d_coeffs, size_t n, size_t domain_extension, void* stream);
+
+/* bb/plonk/proof_system/prover/c_bind.cpp:101-121 */
+void* bbg_new_evaluation_domain(size_t circuit_size);
+void bbg_delete_evaluation_domain(void* domain);
+int bbg_ifft(void* coeffs, void* domain);
+int bbg_coset_fft_with_generator_shift(void* coeffs, const void* constant, void* domain);
+/* evaluation_domain constants (bb/polynomials/evaluation_domain.cpp:57-76): root, root_inverse, domain,
+ * domain_inverse, generator, generator_inverse -- 6 x 32 B, computed by the library's own host arithmetic */
+int bbg_domain_constants(size_t n, void* out6);
+
+/* element-wise probe used by the L0 parity tests: out[i] = op(a[i], b[i]) on the device.
+ * field: 0 fq, 1 fr.  op: 0 mul 1 add 2 sub 3 sqr 4 to_montgomery 5 from_montgomery 7 reduce_once 8 neg */
+int bbg_field_op(int field, int op, const void* a, const void* b, void* out, size_t n);
+/* g1 probe: op 0 mixed add (jac, affine) 1 add (jac, jac) 2 dbl (jac); inputs/outputs 96-byte Jacobian */
+int bbg_g1_op(int op, const void* a, const void* b, void* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBG_H */
