@@ -48,6 +48,7 @@ static int create_context(int device)
     cudaDeviceProp prop;
     BBG_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
+    if (getenv("BBG_STACK")) BBG_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(getenv("BBG_STACK"))));
     BBG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     BBG_CUDA(cudaEventCreate(&c->ev_a));
     BBG_CUDA(cudaEventCreate(&c->ev_b));
@@ -85,8 +86,9 @@ struct DeviceTimer {
 
 // ---- Pippenger object: the SRS resident in HBM as n contiguous affine points
 struct PippengerObj {
-    affine_t* d_points = nullptr;
+    affine_t* d_points = nullptr;     // level 0 = the n SRS points; levels 1..L-1 follow (msm.cu k_msm_precompute)
     size_t n = 0;
+    MsmLevels lv;
     const void* host_table = nullptr; // adopted 2n host table (for pointer recognition), may be null
 };
 static std::vector<PippengerObj*> g_pippengers;
@@ -167,7 +169,11 @@ static PippengerObj* new_obj(Context* ctx, size_t n)
 {
     PippengerObj* o = new PippengerObj();
     o->n = n;
-    if (cudaMalloc(&o->d_points, std::max<size_t>(n, 1) * 64) != cudaSuccess) {
+    // fixed-base levels: as many as fit in half of the free HBM (all of them for every size the prover uses)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)8 << 30;
+    o->lv = msm_levels_plan(std::max<size_t>(n, 1), free_b / 2);
+    if (cudaMalloc(&o->d_points, std::max<size_t>(n, 1) * 64 * o->lv.L) != cudaSuccess) {
         set_last_error("cudaMalloc failed for SRS points");
         delete o;
         return nullptr;
@@ -379,6 +385,28 @@ int bbg_device_count(void)
 uint64_t bbg_kernel_launches(void) { return g_ctx ? g_ctx->launches : 0; }
 double bbg_last_device_ms(void) { return g_ctx ? g_ctx->last_kernel_ms : 0.0; }
 
+int bbg_profile(int enable)
+{
+    GET_CTX();
+    ctx->prof.on = enable != 0;
+    ctx->prof.n = 0;
+    return BBG_OK;
+}
+int bbg_profile_read(double* ms, int n)
+{
+    GET_CTX();
+    for (int i = 0; i < n; ++i) ms[i] = 0.0;
+    Profiler& pr = ctx->prof;
+    if (pr.n < 2) return BBG_OK;
+    BBG_CUDA(cudaEventSynchronize(pr.ev[pr.n - 1]));
+    for (int i = 0; i + 1 < pr.n; ++i) {
+        float t = 0.f;
+        BBG_CUDA(cudaEventElapsedTime(&t, pr.ev[i], pr.ev[i + 1]));
+        if (pr.ids[i] >= 0 && pr.ids[i] < n) ms[pr.ids[i]] += t;
+    }
+    return BBG_OK;
+}
+
 void* bbg_malloc(size_t size)
 {
     Context* ctx = nullptr;
@@ -398,6 +426,7 @@ void bbg_free(void* ptr)
 // ---- Pippenger objects
 static void* finish_obj(Context* ctx, PippengerObj* o, int rc)
 {
+    if (rc == BBG_OK) rc = msm_precompute_device(ctx, o->d_points, o->n, o->lv, ctx->stream);
     if (rc == BBG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         set_last_error("stream sync failed while building the SRS");
         rc = BBG_ERR_CUDA;
@@ -497,14 +526,15 @@ int bbg_pippenger_get_point_table(void* pippenger, void* table2n_out)
     return rc;
 }
 
-static int msm_host_scalars(Context* ctx, const void* scalars, size_t n, const affine_t* d_points, size_t stride, void* result)
+static int msm_host_scalars(Context* ctx, const void* scalars, size_t n, const affine_t* d_points, size_t stride, const MsmLevels& lv,
+                            size_t base, void* result)
 {
     int rc;
     if ((rc = ctx->msm_scalars.reserve(std::max<size_t>(n, 1) * 32))) return rc;
     if ((rc = ctx->msm_result.reserve(96))) return rc;
     if (n) BBG_CUDA(cudaMemcpyAsync(ctx->msm_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     DeviceTimer tm(ctx);
-    if ((rc = msm_device(ctx, ctx->msm_scalars.p, n, d_points, stride, ctx->msm_result.p, ctx->stream))) return rc;
+    if ((rc = msm_device(ctx, ctx->msm_scalars.p, n, d_points, stride, lv, base, ctx->msm_result.p, ctx->stream))) return rc;
     BBG_CUDA(cudaMemcpyAsync(result, ctx->msm_result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
     return tm.finish();
 }
@@ -521,7 +551,7 @@ int bbg_pippenger_unsafe(void* pippenger, const void* scalars, size_t from, size
         set_last_error("pippenger_unsafe: [from, from+range) exceeds the SRS");
         return BBG_ERR_SRS;
     }
-    return msm_host_scalars(ctx, scalars, range, o->d_points + from, 1, result);
+    return msm_host_scalars(ctx, scalars, range, o->d_points, 1, o->lv, from, result);
 }
 
 int bbg_pippenger_unsafe_dev(void* pippenger, const void* d_scalars, size_t from, size_t range, void* d_result, void* stream)
@@ -536,7 +566,7 @@ int bbg_pippenger_unsafe_dev(void* pippenger, const void* d_scalars, size_t from
         set_last_error("pippenger_unsafe: [from, from+range) exceeds the SRS");
         return BBG_ERR_SRS;
     }
-    return msm_device(ctx, d_scalars, range, o->d_points + from, 1, d_result, (cudaStream_t)stream);
+    return msm_device(ctx, d_scalars, range, o->d_points, 1, o->lv, from, d_result, (cudaStream_t)stream);
 }
 
 int bbg_pippenger(const void* scalars, const void* points_table2n, size_t num_points, int handle_edge_cases, void* result)
@@ -554,14 +584,14 @@ int bbg_pippenger(const void* scalars, const void* points_table2n, size_t num_po
         if (base && p >= base && p < base + o->n * 128 && (size_t)(p - base) % 128 == 0) {
             size_t from = (size_t)(p - base) / 128;
             if (from + num_points <= o->n) {
-                return msm_host_scalars(ctx, scalars, num_points, o->d_points + from, 1, result);
+                return msm_host_scalars(ctx, scalars, num_points, o->d_points, 1, o->lv, from, result);
             }
         }
     }
     int rc;
     if ((rc = ctx->msm_points.reserve(std::max<size_t>(num_points, 1) * 64))) return rc;
     if (num_points && (rc = upload_even_entries(ctx, points_table2n, num_points, (affine_t*)ctx->msm_points.p))) return rc;
-    return msm_host_scalars(ctx, scalars, num_points, (const affine_t*)ctx->msm_points.p, 1, result);
+    return msm_host_scalars(ctx, scalars, num_points, (const affine_t*)ctx->msm_points.p, 1, MsmLevels(), 0, result);
 }
 
 int bbg_msm_points(const void* scalars, const void* points, size_t num_points, void* result)
@@ -574,13 +604,13 @@ int bbg_msm_points(const void* scalars, const void* points, size_t num_points, v
     int rc;
     if ((rc = ctx->msm_points.reserve(std::max<size_t>(num_points, 1) * 64))) return rc;
     if (num_points) BBG_CUDA(cudaMemcpyAsync(ctx->msm_points.p, points, num_points * 64, cudaMemcpyHostToDevice, ctx->stream));
-    return msm_host_scalars(ctx, scalars, num_points, (const affine_t*)ctx->msm_points.p, 1, result);
+    return msm_host_scalars(ctx, scalars, num_points, (const affine_t*)ctx->msm_points.p, 1, MsmLevels(), 0, result);
 }
 
 int bbg_msm_points_dev(const void* d_scalars, const void* d_points, size_t point_stride, size_t num_points, void* d_result, void* stream)
 {
     GET_CTX();
-    return msm_device(ctx, d_scalars, num_points, d_points, point_stride ? point_stride : 1, d_result, (cudaStream_t)stream);
+    return msm_device(ctx, d_scalars, num_points, d_points, point_stride ? point_stride : 1, MsmLevels(), 0, d_result, (cudaStream_t)stream);
 }
 
 int bbg_generate_pippenger_point_table(const void* points, void* table, size_t num_points)

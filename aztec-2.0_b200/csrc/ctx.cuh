@@ -54,7 +54,28 @@ struct DevBuf {
     }
 };
 
-struct NttTables; // ntt.cu
+// Optional per-phase device timing (bbg_profile): CUDA events recorded on the launching stream at
+// phase boundaries; bench.py reads the per-phase milliseconds for the roofline of the dominant kernel.
+enum Phase {
+    PH_MSM_DIGITS = 0, PH_MSM_SCAN, PH_MSM_SCATTER, PH_MSM_ACCUMULATE, PH_MSM_FIXUP, PH_MSM_REDUCE, PH_MSM_COMBINE,
+    PH_NTT_TABLES, PH_NTT_PASS0, PH_NTT_PASS1, PH_NTT_PASS2, PH_NTT_PASS3, PH_COUNT
+};
+struct Profiler {
+    static constexpr int MAX_MARKS = 64;
+    bool on = false;
+    int n = 0;
+    int ids[MAX_MARKS];
+    cudaEvent_t ev[MAX_MARKS] = {};
+    void begin() { n = 0; }
+    // marks the START of phase `id` (id < 0: end of the last phase)
+    void mark(cudaStream_t st, int id)
+    {
+        if (!on || n >= MAX_MARKS) return;
+        if (ev[n] == nullptr) cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], st);
+        ids[n++] = id;
+    }
+};
 
 struct Context {
     int device = -1;
@@ -71,6 +92,7 @@ struct Context {
     // pinned staging for small results
     void* pinned = nullptr;
     size_t pinned_cap = 0;
+    Profiler prof;
     uint64_t launches = 0; // kernels launched by this library (bench.py reports it)
     double last_kernel_ms = 0.0;
     std::mutex mu;

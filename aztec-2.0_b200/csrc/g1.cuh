@@ -86,7 +86,7 @@ __device__ __forceinline__ void xyzz_store(xyzz_t* p, const xyzz_t& v)
 }
 
 // 2 * (x, y) for an affine point, result in XYZZ ("mdbl-2008-s-1", a = 0): 2M + 5S... here 3M + 4S
-static __device__ __noinline__ xyzz_t xyzz_dbl_affine(const affine_t& p)
+__device__ __forceinline__ xyzz_t xyzz_dbl_affine(const affine_t& p)
 {
     xyzz_t r;
     fq u = fe_dbl(p.y);           // U = 2 y
@@ -102,7 +102,7 @@ static __device__ __noinline__ xyzz_t xyzz_dbl_affine(const affine_t& p)
     return r;
 }
 // 2 * P in XYZZ ("dbl-2008-s-1", a = 0)
-static __device__ __noinline__ xyzz_t xyzz_dbl(const xyzz_t& p)
+__device__ __forceinline__ xyzz_t xyzz_dbl(const xyzz_t& p)
 {
     if (xyzz_is_inf(p)) {
         return p;
@@ -154,8 +154,11 @@ __device__ __forceinline__ void xyzz_madd(xyzz_t& acc, const affine_t& b)
     acc.zzz = fe_mul(acc.zzz, ppp);
 }
 
-// a += b, both XYZZ ("add-2008-s": 12M + 2S), all exceptional cases handled
-static __device__ __noinline__ void xyzz_add(xyzz_t& a, const xyzz_t& b)
+// a += b, both XYZZ ("add-2008-s": 12M + 2S), all exceptional cases handled.
+// Everything in this header is force-inlined: a __noinline__ helper called from a divergent branch was
+// observed (compute-sanitizer, sm_100a, CUDA 12.9) to clobber a uniform register that the other
+// lanes of the warp still needed, so the kernels keep ONE inlined add site per loop instead of calls.
+__device__ __forceinline__ void xyzz_add(xyzz_t& a, const xyzz_t& b)
 {
     if (xyzz_is_inf(b)) {
         return;
@@ -187,6 +190,70 @@ static __device__ __noinline__ void xyzz_add(xyzz_t& a, const xyzz_t& b)
     a.y = y3;
     a.zz = fe_mul(fe_mul(a.zz, b.zz), pp);
     a.zzz = fe_mul(fe_mul(a.zzz, b.zzz), ppp);
+}
+
+// lane-to-lane move of a whole point (warp-shuffle g1 reductions)
+__device__ __forceinline__ xyzz_t xyzz_shfl_down(const xyzz_t& p, int delta)
+{
+    xyzz_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, p.x.l[i], delta);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, p.y.l[i], delta);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, p.zz.l[i], delta);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, p.zzz.l[i], delta);
+    }
+    return r;
+}
+// c ? a : b, limb-wise (keeps both operands in registers; no local-memory indexing)
+__device__ __forceinline__ xyzz_t xyzz_select(bool c, const xyzz_t& a, const xyzz_t& b)
+{
+    xyzz_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = c ? a.x.l[i] : b.x.l[i];
+        r.y.l[i] = c ? a.y.l[i] : b.y.l[i];
+        r.zz.l[i] = c ? a.zz.l[i] : b.zz.l[i];
+        r.zzz.l[i] = c ? a.zzz.l[i] : b.zzz.l[i];
+    }
+    return r;
+}
+
+// a^(p-2) (field_impl.hpp:323-329 invert = pow(modulus - 2)); plain square-and-multiply, loop kept rolled
+template <class F> __device__ __forceinline__ Fe<F> fe_inv(const Fe<F>& a)
+{
+    Fe<F> acc = fe_one<F>();
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = F::P(i);
+    e[0] -= 2; // both moduli end in ...47 / ...01: no borrow
+#pragma unroll 1
+    for (int i = 253; i >= 0; --i) {
+        acc = fe_sqr(acc);
+        uint32_t limb = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) limb = (i >> 5) == k ? e[k] : limb;
+        if ((limb >> (i & 31)) & 1) {
+            acc = fe_mul(acc, a);
+        }
+    }
+    return acc;
+}
+
+// XYZZ -> affine (x = X / ZZ, y = Y / ZZZ) with one field inversion; infinity keeps barretenberg's flag
+__device__ __forceinline__ affine_t xyzz_to_affine(const xyzz_t& p)
+{
+    affine_t r;
+    if (xyzz_is_inf(p)) {
+        r.x = fe_zero<FqParams>();
+        r.y = fe_zero<FqParams>();
+        r.x.l[7] |= INF_BIT;
+        return r;
+    }
+    fq inv = fe_inv(fe_mul(p.zz, p.zzz));      // 1 / (ZZ * ZZZ)
+    r.x = fe_reduce_once(fe_mul(p.x, fe_mul(inv, p.zzz)));
+    r.y = fe_reduce_once(fe_mul(p.y, fe_mul(inv, p.zz)));
+    return r;
 }
 
 // XYZZ -> the reference's 96-byte Jacobian element: with Z := ZZZ we have Z^2 = ZZ^3, Z^3 = ZZZ^3,

@@ -6,7 +6,17 @@
 namespace bbg {
 
 // msm.cu
-int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_points, size_t point_stride, void* d_out, cudaStream_t st);
+// Fixed-base levels of a Pippenger object: entry l * stride + i holds 2^(D l) * P_i.  L == 1: plain points.
+struct MsmLevels {
+    unsigned L = 1;    // levels held in HBM
+    unsigned D = 0;    // bits between consecutive levels (a multiple of c)
+    unsigned c = 0;    // window bits the levels were built for
+    size_t stride = 0; // table entries per level
+};
+MsmLevels msm_levels_plan(size_t n, size_t max_table_bytes);
+int msm_precompute_device(Context* ctx, void* d_table, size_t n, const MsmLevels& lv, cudaStream_t st);
+int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_points, size_t point_stride, const MsmLevels& lv,
+               size_t base, void* d_out, cudaStream_t st);
 int g1_sum_device(Context* ctx, const void* d_jacs, size_t n, void* d_out, cudaStream_t st);
 int srs_decode_device(Context* ctx, const void* d_raw, size_t n, void* d_points, cudaStream_t st);
 int point_table_device(Context* ctx, const void* d_points, size_t n, void* d_table, cudaStream_t st);

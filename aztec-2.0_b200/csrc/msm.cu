@@ -7,61 +7,58 @@
 // reduce_buckets/add_affine_points :305-521 -> evaluate_pippenger_rounds :720-838) is re-thought
 // for the GPU rather than translated:
 //
+//   0. k_msm_precompute      once per SRS (Pippenger object): level l holds 2^(D*l) * P_i in affine form, so
+//                            window w = l*S + r of every scalar can use the SAME S bucket sets (S = 1 when
+//                            all W levels fit in HBM): the per-window bucket reductions and the c*W
+//                            Horner doublings of the textbook method disappear.  [The reference makes the
+//                            same kind of trade at SRS-load time: it doubles the table with the
+//                            endomorphism images, scalar_multiplication.cpp:104-112.]
 //   1. k_msm_digits<false>   scalar -> canonical -> signed c-bit windows, histogram of bucket sizes
-//   2. scan                  bucket sizes -> bucket start offsets (one flat key space: window*B + |digit|-1)
-//   3. k_msm_digits<true>    counting-sort scatter of (point index, sign) by bucket   [order inside a
+//   2. scan                  bucket sizes -> bucket start offsets (flat key space: set*B + |digit|-1)
+//   3. k_msm_digits<true>    counting-sort scatter of (level-table index, sign) by bucket   [order inside a
 //                            bucket is irrelevant: the group is commutative]
 //   4. k_msm_accumulate      the sorted list is cut into equal-length chunks, one per thread, so
 //                            every thread does the same number of mixed additions no matter how
-//                            skewed the scalar distribution is; buckets cut by a chunk boundary leave
-//                            partial sums that k_msm_fixup stitches together
-//   5. k_msm_reduce_level    sum_b (b+1)*bucket[b] per window by a log_16-depth hierarchy of
-//                            running sums (the reference's running-sum trick :773-783, parallelised)
-//   6. k_msm_combine         Horner over the windows (c doublings each), XYZZ -> Jacobian
+//                            skewed the scalar distribution is; a bucket cut by a chunk boundary leaves
+//                            partial sums ("slots") that
+//      k_msm_merge           folds, 8 slots per thread, level after level (log depth even when every
+//                            scalar is equal and one bucket holds everything)
+//   5. k_msm_segments        sum_b (b+1)*bucket[b]: running sums over segments of `ell` buckets (the
+//                            reference's running-sum trick :773-783), each segment then shifted to its
+//                            place by a short double-and-add, and
+//      k_msm_tree_sum        a warp-shuffle / shared-memory tree of g1 additions per bucket set
+//   6. k_msm_finish          Horner over the S bucket sets (S = 1: nothing), XYZZ -> Jacobian
 //
-// Arithmetic is integer-ALU bound (IMAD.WIDE); HBM traffic is ~(32 + 64*W) B per point.
+// Arithmetic is integer-pipe bound (IMAD.WIDE at half rate: 70 G fq-mul/s measured on B200); HBM
+// traffic is ~(32 + 68*W) B per point.  No kernel calls a non-inlined device function (see g1.cuh).
+#include <algorithm>
+
 #include "g1.cuh"
 #include "internal.hpp"
 
 namespace bbg {
 
-struct MsmPlan {
-    unsigned c;      // window bits
-    unsigned W;      // number of windows, W*c >= 255 so the top window never carries out
-    unsigned B;      // buckets per window = 2^(c-1) (signed digits)
-    size_t G;        // total buckets W*B
-};
-
-static MsmPlan msm_plan(size_t n)
-{
-    unsigned lg = 0;
-    while (((size_t)1 << (lg + 1)) <= n) {
-        ++lg;
-    }
-    int c = (int)lg - 4;
-    if (c < 2) c = 2;
-    if (c > 20) c = 20;
-    MsmPlan p;
-    p.c = (unsigned)c;
-    p.W = (255 + p.c - 1) / p.c;
-    p.B = 1u << (p.c - 1);
-    p.G = (size_t)p.W * p.B;
-    return p;
-}
-
 // ------------------------------------------------------------------------------------------------
 // 1/3. digits: histogram (SCATTER = false) or counting-sort scatter (SCATTER = true)
 // ------------------------------------------------------------------------------------------------
+struct DigitParams {
+    uint32_t n;
+    uint32_t c;            // window bits
+    uint32_t W;            // windows
+    uint32_t S;            // bucket sets (windows per level)
+    uint32_t B;            // buckets per set = 2^(c-1)
+    uint32_t level_stride; // table entries between consecutive levels
+    uint32_t base;         // table entry of scalar 0 (Pippenger `from`)
+};
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_msm_digits(const fr_t* __restrict__ scalars,
-                                                    uint32_t n,
-                                                    unsigned c,
-                                                    unsigned W,
+                                                    const DigitParams P,
                                                     uint32_t* __restrict__ counters,
                                                     uint32_t* __restrict__ sorted)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) {
+    if (i >= P.n) {
         return;
     }
     // from_montgomery_form => canonical integer in [0, r)  (scalar_multiplication.cpp:224)
@@ -70,26 +67,38 @@ __global__ void __launch_bounds__(256) k_msm_digits(const fr_t* __restrict__ sca
 #pragma unroll
     for (int j = 0; j < 8; ++j) k[j] = s.l[j];
     k[8] = 0;
-    const uint32_t B = 1u << (c - 1);
+    const uint32_t c = P.c;
+    const uint32_t half = 1u << (c - 1);
     const uint32_t mask = (1u << c) - 1;
     uint32_t carry = 0;
-    for (unsigned w = 0; w < W; ++w) {
+    uint32_t level = 0, set = 0;
+    for (unsigned w = 0; w < P.W; ++w) {
         unsigned pos = w * c;
         unsigned limb = pos >> 5, off = pos & 31;
-        uint64_t two = (uint64_t)k[limb] | ((uint64_t)k[limb + 1] << 32);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            lo = limb == (unsigned)j ? k[j] : lo;
+            hi = limb == (unsigned)j ? k[j + 1] : hi;
+        }
+        uint64_t two = (uint64_t)lo | ((uint64_t)hi << 32);
         uint32_t v = ((uint32_t)(two >> off) & mask) + carry;
-        // signed digit in (-B, B]: v > B  =>  digit v - 2^c, borrow one from the next window
-        uint32_t neg = v > B ? 1u : 0u;
+        // signed digit in (-2^(c-1), 2^(c-1)]: v > half  =>  digit v - 2^c, borrow one from the next window
+        uint32_t neg = v > half ? 1u : 0u;
         uint32_t mag = neg ? (mask + 1 - v) : v;
         carry = neg;
         if (mag) {
-            uint32_t g = w * B + (mag - 1);
+            uint32_t g = set * P.B + (mag - 1);
             if (SCATTER) {
                 uint32_t dst = atomicAdd(&counters[g], 1u);
-                sorted[dst] = (i << 1) | neg;
+                sorted[dst] = ((level * P.level_stride + P.base + i) << 1) | neg;
             } else {
                 atomicAdd(&counters[g], 1u);
             }
+        }
+        if (++set == P.S) {
+            set = 0;
+            ++level;
         }
     }
 }
@@ -196,13 +205,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
 // ------------------------------------------------------------------------------------------------
 // 4. bucket accumulation over equal-length chunks of the bucket-sorted list
 // ------------------------------------------------------------------------------------------------
-struct alignas(16) Partial {
+// A "slot" is the partial sum of a bucket whose entries straddle a chunk boundary.  Every worker
+// emits exactly two: slot[2t] (the run that continues from the previous worker) and slot[2t+1] (the run that
+// continues into the next).  Consecutive slots of one bucket are therefore adjacent, and a worker
+// whose whole range lies inside one bucket emits (sum, identity) so the chain is never broken.
+struct alignas(16) Slot {
     xyzz_t acc;
-    int32_t bucket; // -1: none
-    int32_t pad[3];
+    uint32_t bucket; // SLOT_NONE: empty
+    uint32_t pad[3];
 };
-
+static constexpr uint32_t SLOT_NONE = 0xffffffffu;
 static constexpr int ACC_THREADS = 128;
+static constexpr uint32_t MERGE_K = 8;
+
+__device__ __forceinline__ void slot_store(Slot* s, const xyzz_t& v, uint32_t bucket)
+{
+    xyzz_store(&s->acc, v);
+    s->bucket = bucket;
+}
 
 __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t key)
 {
@@ -223,29 +243,35 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_msm_accumulate(const uint32_
                                                                    const uint32_t* __restrict__ offsets, // G+1
                                                                    uint32_t G,
                                                                    uint32_t chunk,
+                                                                   uint32_t num_chunks,
                                                                    const affine_t* __restrict__ points,
                                                                    uint32_t point_stride,
                                                                    xyzz_t* __restrict__ buckets,
-                                                                   Partial* __restrict__ heads,
-                                                                   Partial* __restrict__ tails)
+                                                                   Slot* __restrict__ slots,
+                                                                   uint32_t* __restrict__ pending)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_chunks) {
+        return;
+    }
+    Slot* slot_a = slots + 2 * (size_t)t;
+    Slot* slot_b = slot_a + 1;
     const uint32_t total = __ldg(offsets + G); // number of non-zero digits, produced by the scan
     const uint64_t start64 = (uint64_t)t * chunk;
     if (start64 >= total) {
+        slot_a->bucket = SLOT_NONE;
+        slot_b->bucket = SLOT_NONE;
         return;
     }
     const uint32_t start = (uint32_t)start64;
     const uint32_t end = (start64 + chunk < total) ? start + chunk : total;
-
-    heads[t].bucket = -1;
-    tails[t].bucket = -1;
 
     // the (non-empty) bucket that contains position `start`
     uint32_t g = upper_bound_u32(offsets, G + 1, start) - 1;
     uint32_t g_begin = __ldg(offsets + g);
     uint32_t g_end = __ldg(offsets + g + 1);
 
+    bool a_set = false, b_set = false;
     xyzz_t acc = xyzz_infinity();
     uint32_t pos = start;
     uint32_t v = __ldg(sorted + pos);
@@ -267,16 +293,19 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_msm_accumulate(const uint32_
         }
         ++pos;
         if (pos == g_end || pos == end) {
-            // flush
-            const bool complete = (g_begin >= start) && (g_end <= end);
-            if (complete) {
+            const bool cont_l = g_begin < start; // bucket began in an earlier chunk
+            const bool cont_r = g_end > end;     // bucket continues into a later chunk
+            if (!cont_l && !cont_r) {
                 xyzz_store(buckets + g, acc);
-            } else if (g_begin < start) {
-                heads[t].acc = acc; // bucket began in an earlier chunk
-                heads[t].bucket = (int32_t)g;
             } else {
-                tails[t].acc = acc; // bucket continues into a later chunk
-                tails[t].bucket = (int32_t)g;
+                if (cont_l) {
+                    slot_store(slot_a, acc, g);
+                    a_set = true;
+                }
+                if (cont_r) {
+                    slot_store(slot_b, cont_l ? xyzz_infinity() : acc, g);
+                    b_set = true;
+                }
             }
             if (pos == end) {
                 break;
@@ -292,92 +321,190 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_msm_accumulate(const uint32_
         v = vn;
         pt = ptn;
     }
+    if (!a_set) slot_a->bucket = SLOT_NONE;
+    if (!b_set) slot_b->bucket = SLOT_NONE;
+    if (a_set || b_set) {
+        atomicAdd(pending, 1u); // something for the merge levels to do
+    }
 }
 
-// one thread per chunk whose tail opens a cut bucket: add the heads of the following chunks
-__global__ void __launch_bounds__(128) k_msm_fixup(uint32_t num_chunks,
-                                                    const Partial* __restrict__ heads,
-                                                    const Partial* __restrict__ tails,
-                                                    xyzz_t* __restrict__ buckets)
+// One merge level: worker u folds slots [u*K + 1, (u+1)*K + 1) (worker 0 also takes slot 0), i.e. the
+// boundary falls between the two slots of one chunk so the typical (tail, next head) pair is never cut.
+__global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
+                                                    uint32_t n_in,
+                                                    uint32_t workers,
+                                                    const uint32_t* __restrict__ pending_in,
+                                                    xyzz_t* __restrict__ buckets,
+                                                    Slot* __restrict__ out,
+                                                    uint32_t* __restrict__ pending_out)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= num_chunks) {
+    if (__ldg(pending_in) == 0) {
+        return; // the previous level left nothing open (the usual case after the first merge)
+    }
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= workers) {
         return;
     }
-    const int32_t g = tails[t].bucket;
-    if (g < 0) {
-        return;
-    }
-    xyzz_t acc = xyzz_load(&tails[t].acc);
-    for (uint32_t u = t + 1; u < num_chunks && heads[u].bucket == g; ++u) {
-        xyzz_t h = xyzz_load(&heads[u].acc);
-        xyzz_add(acc, h);
-    }
-    xyzz_store(buckets + g, acc);
-}
+    const uint32_t lo = u == 0 ? 0 : u * MERGE_K + 1;
+    uint32_t hi = (u + 1) * MERGE_K + 1;
+    if (hi > n_in || u + 1 == workers) hi = n_in;
+    Slot* out_a = out + 2 * (size_t)u;
+    Slot* out_b = out_a + 1;
+    bool a_set = false, b_set = false;
 
-// ------------------------------------------------------------------------------------------------
-// 5. bucket reduction.  Invariant per window:  sum_i i * X0[i]  ==  sum_i ( scale_k * i * R_k[i] + C_k[i] )
-//    with scale_k = prod of the segment lengths of the levels below.  One thread folds `ell` entries.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_msm_reduce_level(const xyzz_t* __restrict__ r_in,
-                                                          const xyzz_t* __restrict__ c_in, // may be null (level 0)
-                                                          uint32_t m_in,                   // entries per window
-                                                          uint32_t ell,                    // segment length (power of 2)
-                                                          uint32_t log_scale,              // log2(scale_k)
-                                                          uint32_t num_windows,
-                                                          xyzz_t* __restrict__ r_out,
-                                                          xyzz_t* __restrict__ c_out)
-{
-    const uint32_t m_out = m_in / ell;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m_out * num_windows) {
-        return;
-    }
-    const uint32_t w = t / m_out, s = t % m_out;
-    const xyzz_t* r = r_in + (size_t)w * m_in + (size_t)s * ell;
-    xyzz_t run = xyzz_infinity(), acc = xyzz_infinity();
-    for (uint32_t j = ell - 1; j >= 1; --j) {
-        xyzz_t x = xyzz_load(r + j);
-        xyzz_add(run, x);
-        xyzz_add(acc, run);
-    }
-    {
-        xyzz_t x = xyzz_load(r);
-        xyzz_add(run, x);
-    }
-    for (uint32_t d = 0; d < log_scale; ++d) {
-        acc = xyzz_dbl(acc);
-    }
-    if (c_in != nullptr) {
-        const xyzz_t* cc = c_in + (size_t)w * m_in + (size_t)s * ell;
-        for (uint32_t j = 0; j < ell; ++j) {
-            xyzz_t x = xyzz_load(cc + j);
-            xyzz_add(acc, x);
+    xyzz_t acc = xyzz_infinity();
+    uint32_t run_bucket = SLOT_NONE;
+    uint32_t run_start = lo;
+    for (uint32_t i = lo; i <= hi; ++i) {
+        const uint32_t b = i < hi ? in[i].bucket : SLOT_NONE;
+        const bool close = run_bucket != SLOT_NONE && (i == hi || b != run_bucket);
+        if (close) {
+            const bool cont_l = run_start == lo && lo > 0 && in[lo - 1].bucket == run_bucket;
+            const bool cont_r = i == hi && hi < n_in && in[hi].bucket == run_bucket;
+            if (!cont_l && !cont_r) {
+                xyzz_store(buckets + run_bucket, acc);
+            } else {
+                if (cont_l) {
+                    slot_store(out_a, acc, run_bucket);
+                    a_set = true;
+                }
+                if (cont_r) {
+                    slot_store(out_b, cont_l ? xyzz_infinity() : acc, run_bucket);
+                    b_set = true;
+                }
+            }
+            run_bucket = SLOT_NONE;
+        }
+        if (i < hi && b != SLOT_NONE) {
+            xyzz_t x = xyzz_load(&in[i].acc);
+            if (run_bucket == SLOT_NONE) {
+                run_bucket = b;
+                run_start = i;
+                acc = x;
+            } else {
+                xyzz_add(acc, x); // the one inlined add site of this kernel
+            }
         }
     }
-    xyzz_store(r_out + (size_t)w * m_out + s, run);
-    xyzz_store(c_out + (size_t)w * m_out + s, acc);
+    if (!a_set) out_a->bucket = SLOT_NONE;
+    if (!b_set) out_b->bucket = SLOT_NONE;
+    if (a_set || b_set) {
+        atomicAdd(pending_out, 1u);
+    }
 }
 
-// 6. result = sum_w 2^(c w) * (C_w + R_w)   [bucket b (0-based) carries weight b+1 = i + 1]
-__global__ void k_msm_combine(const xyzz_t* __restrict__ r_top,
-                              const xyzz_t* __restrict__ c_top,
-                              uint32_t num_windows,
-                              uint32_t c,
-                              jac_t* __restrict__ out)
+// ------------------------------------------------------------------------------------------------
+// 5. bucket reduction: sum over b of (b + 1) * bucket[b] per set
+// ------------------------------------------------------------------------------------------------
+// Worker (set, seg): running sums over buckets [seg*ell, (seg+1)*ell):  R = sum x_j,  A = sum (j+1) x_j,
+// then V = A + (seg*ell) * R by double-and-add.  One add site: the loop alternates run += x / acc += run.
+__global__ void __launch_bounds__(128) k_msm_segments(const xyzz_t* __restrict__ buckets,
+                                                       uint32_t B,   // buckets per set
+                                                       uint32_t ell, // segment length (divides B)
+                                                       uint32_t num_workers,
+                                                       xyzz_t* __restrict__ out)
 {
-    if (blockIdx.x != 0 || threadIdx.x != 0) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_workers) {
+        return;
+    }
+    const uint32_t segs = B / ell;
+    const uint32_t set = t / segs, seg = t % segs;
+    const xyzz_t* src = buckets + (size_t)set * B + (size_t)seg * ell;
+    xyzz_t run = xyzz_infinity(), acc = xyzz_infinity();
+    for (uint32_t step = 0; step < 2 * ell; ++step) {
+        const bool second = step & 1;
+        xyzz_t rhs;
+        if (!second) {
+            rhs = xyzz_load(src + (ell - 1 - (step >> 1)));
+        } else {
+            rhs = run;
+        }
+        xyzz_t lhs = xyzz_select(second, acc, run);
+        xyzz_add(lhs, rhs);
+        if (second) {
+            acc = lhs;
+        } else {
+            run = lhs;
+        }
+    }
+    // V = acc + (seg * ell) * run
+    const uint32_t k = seg * ell;
+    if (k != 0 && !xyzz_is_inf(run)) {
+        const int msb = 31 - __clz(k);
+        xyzz_t m = run;
+        for (int bit = msb - 1; bit >= -1; --bit) {
+            xyzz_t rhs;
+            bool do_add;
+            if (bit >= 0) {
+                m = xyzz_dbl(m);
+                rhs = run;
+                do_add = (k >> bit) & 1;
+            } else {
+                rhs = acc; // last step: fold in A
+                do_add = true;
+            }
+            if (do_add) {
+                xyzz_add(m, rhs);
+            }
+        }
+        acc = m;
+    }
+    xyzz_store(out + t, acc);
+}
+
+// Sum of m consecutive XYZZ points per row: grid (parts, rows); each CTA strides over its share and
+// finishes with a warp-shuffle tree + one shared-memory hop.  out[row * parts + part].
+static constexpr int TREE_THREADS = 256;
+__global__ void __launch_bounds__(TREE_THREADS) k_msm_tree_sum(const xyzz_t* __restrict__ in, uint32_t m, xyzz_t* __restrict__ out)
+{
+    __shared__ xyzz_t sm[TREE_THREADS / 32];
+    const uint32_t parts = gridDim.x, part = blockIdx.x, row = blockIdx.y;
+    const xyzz_t* src = in + (size_t)row * m;
+    const uint32_t per = (m + parts - 1) / parts;
+    const uint32_t lo = part * per;
+    const uint32_t hi = min(lo + per, m);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    xyzz_t acc = xyzz_infinity();
+    const uint32_t iters = (per + TREE_THREADS - 1) / TREE_THREADS;
+    // steps [0, iters): strided loads; next 5: shuffle tree inside each warp; last 5: warp 0 folds the warp sums
+    for (uint32_t step = 0; step < iters + 10; ++step) {
+        xyzz_t rhs = xyzz_infinity();
+        if (step < iters) {
+            const uint32_t i = lo + step * TREE_THREADS + threadIdx.x;
+            if (i < hi) rhs = xyzz_load(src + i);
+        } else {
+            const uint32_t s = (step - iters) % 5;
+            if (step == iters + 5) {
+                if (lane == 0) sm[warp] = acc;
+                __syncthreads();
+                acc = (warp == 0 && lane < TREE_THREADS / 32) ? sm[lane] : xyzz_infinity();
+            }
+            rhs = xyzz_shfl_down(acc, 16 >> s);
+            if (lane + (16 >> s) >= 32) rhs = xyzz_infinity();
+        }
+        xyzz_add(acc, rhs);
+    }
+    if (threadIdx.x == 0) {
+        xyzz_store(out + (size_t)row * parts + part, acc);
+    }
+}
+
+// 6. result = sum_r 2^(c r) * set_sum[r], XYZZ -> Jacobian
+__global__ void __launch_bounds__(32) k_msm_finish(const xyzz_t* __restrict__ set_sums, uint32_t S, uint32_t c, jac_t* __restrict__ out)
+{
+    if (threadIdx.x != 0) {
         return;
     }
     xyzz_t acc = xyzz_infinity();
-    for (int w = (int)num_windows - 1; w >= 0; --w) {
-        for (uint32_t d = 0; d < c; ++d) {
-            acc = xyzz_dbl(acc);
+    for (int r = (int)S - 1; r >= 0; --r) {
+        if (r != (int)S - 1) {
+            for (uint32_t d = 0; d < c; ++d) {
+                acc = xyzz_dbl(acc);
+            }
         }
-        xyzz_t s = xyzz_load(c_top + w);
-        xyzz_t r = xyzz_load(r_top + w);
-        xyzz_add(s, r);
+        xyzz_t s = xyzz_load(set_sums + r);
         xyzz_add(acc, s);
     }
     jac_t j = xyzz_to_jacobian(acc);
@@ -396,39 +523,56 @@ __global__ void k_set_infinity(jac_t* out)
 
 // sum of Jacobian elements (bb/ecc/curves/bn254/scalar_multiplication/c_bind.cpp:40-45 g1_sum);
 // one warp: lanes stride over the inputs, then a shuffle tree of g1 additions.
-__device__ __forceinline__ xyzz_t xyzz_shfl_down(const xyzz_t& p, int delta)
-{
-    xyzz_t r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        r.x.l[i] = __shfl_down_sync(0xffffffffu, p.x.l[i], delta);
-        r.y.l[i] = __shfl_down_sync(0xffffffffu, p.y.l[i], delta);
-        r.zz.l[i] = __shfl_down_sync(0xffffffffu, p.zz.l[i], delta);
-        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, p.zzz.l[i], delta);
-    }
-    return r;
-}
 __global__ void __launch_bounds__(32) k_g1_sum(const jac_t* __restrict__ in, uint32_t n, jac_t* __restrict__ out)
 {
     const unsigned lane = threadIdx.x;
     xyzz_t acc = xyzz_infinity();
-    for (uint32_t i = lane; i < n; i += 32) {
-        jac_t j;
-        j.x = fe_load<FqParams>(&in[i].x);
-        j.y = fe_load<FqParams>(&in[i].y);
-        j.z = fe_load<FqParams>(&in[i].z);
-        xyzz_t p = xyzz_from_jacobian(j);
-        xyzz_add(acc, p);
-    }
-    for (int d = 16; d >= 1; d >>= 1) {
-        xyzz_t o = xyzz_shfl_down(acc, d);
-        xyzz_add(acc, o);
+    const uint32_t iters = (n + 31) / 32;
+    for (uint32_t step = 0; step < iters + 5; ++step) {
+        xyzz_t rhs = xyzz_infinity();
+        if (step < iters) {
+            const uint32_t i = step * 32 + lane;
+            if (i < n) {
+                jac_t j;
+                j.x = fe_load<FqParams>(&in[i].x);
+                j.y = fe_load<FqParams>(&in[i].y);
+                j.z = fe_load<FqParams>(&in[i].z);
+                rhs = xyzz_from_jacobian(j);
+            }
+        } else {
+            const int d = 16 >> (step - iters);
+            rhs = xyzz_shfl_down(acc, d);
+            if (lane + d >= 32) rhs = xyzz_infinity();
+        }
+        xyzz_add(acc, rhs);
     }
     if (lane == 0) {
         jac_t j = xyzz_to_jacobian(acc);
         fe_store(&out->x, j.x);
         fe_store(&out->y, j.y);
         fe_store(&out->z, j.z);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 0. fixed-base levels: table[l * stride + i] = 2^(D l) * P_i (affine), l = 1 .. L-1 (level 0 = the SRS itself)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_msm_precompute(affine_t* __restrict__ table, uint32_t n, uint32_t stride, uint32_t L, uint32_t D)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    affine_t p = affine_load(table + i);
+    xyzz_t cur = xyzz_from_affine(p);
+    for (uint32_t l = 1; l < L; ++l) {
+        for (uint32_t d = 0; d < D; ++d) {
+            cur = xyzz_dbl(cur);
+        }
+        affine_t a = xyzz_to_affine(cur);
+        fe_store(&table[(size_t)l * stride + i].x, a.x);
+        fe_store(&table[(size_t)l * stride + i].y, a.y);
+        cur = xyzz_from_affine(a); // ZZ = ZZZ = 1 again
     }
 }
 
@@ -518,45 +662,114 @@ static int exclusive_scan(Context* ctx, const uint32_t* d_in, size_t n, uint32_t
     return BBG_OK;
 }
 
-// Device-pointer MSM: d_scalars (n x 32 B), d_points (affine, stride in points), d_out (96 B Jacobian).
-int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_points, size_t point_stride, void* d_out, cudaStream_t st)
+static unsigned env_uint(const char* name, unsigned dflt)
 {
+    const char* v = getenv(name);
+    return v && *v ? (unsigned)atoi(v) : dflt;
+}
+
+static unsigned floor_log2(size_t n)
+{
+    unsigned lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) ++lg;
+    return lg;
+}
+
+// window width for an SRS of `n` points when every level is precomputed (bucket reduction is cheap then)
+static unsigned msm_window_bits(size_t n)
+{
+    int c = (int)floor_log2(n ? n : 1) - 4;
+    if (c < 4) c = 4;
+    if (c > 20) c = 20;
+    return env_uint("BBG_MSM_C", (unsigned)c);
+}
+
+MsmLevels msm_levels_plan(size_t n, size_t max_table_bytes)
+{
+    MsmLevels lv;
+    lv.c = msm_window_bits(n);
+    const unsigned W = (255 + lv.c - 1) / lv.c;
+    unsigned L = env_uint("BBG_MSM_LEVELS", W);
+    if (L > W) L = W;
+    if (L < 1) L = 1;
+    while (L > 1 && (size_t)L * n * 64 > max_table_bytes) --L;
+    const unsigned S = (W + L - 1) / L;
+    lv.L = (W + S - 1) / S;
+    lv.D = S * lv.c;
+    lv.stride = n;
+    return lv;
+}
+
+int msm_precompute_device(Context* ctx, void* d_table, size_t n, const MsmLevels& lv, cudaStream_t st)
+{
+    if (lv.L <= 1 || n == 0) return BBG_OK;
+    k_msm_precompute<<<div_up(n, 128), 128, 0, st>>>((affine_t*)d_table, (uint32_t)n, (uint32_t)lv.stride, lv.L, lv.D);
+    ctx->launches += 1;
+    BBG_CUDA(cudaGetLastError());
+    return BBG_OK;
+}
+
+// Device-pointer MSM over table entries [base, base + n) of level 0 (and the same range of every other level).
+//   lv.L == 1: plain points (any stride), W bucket sets.   lv.L > 1: fixed-base levels, S = D / c bucket sets.
+int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_points, size_t point_stride, const MsmLevels& lv_in,
+               size_t base, void* d_out, cudaStream_t st)
+{
+    Profiler& pr = ctx->prof;
+    pr.begin();
     if (n == 0) {
         k_set_infinity<<<1, 1, 0, st>>>((jac_t*)d_out);
         ctx->launches += 1;
         BBG_CUDA(cudaGetLastError());
         return BBG_OK;
     }
-    if (n >= (1ull << 31)) {
-        set_last_error("msm: n must be < 2^31");
-        return BBG_ERR_ARG;
+    MsmLevels lv = lv_in;
+    if (lv.L <= 1) {
+        lv.L = 1;
+        lv.c = env_uint("BBG_MSM_C1", (unsigned)std::max(2, std::min(16, (int)floor_log2(n) - 4)));
+        lv.stride = 0;
     }
-    const MsmPlan pl = msm_plan(n);
-    const size_t max_entries = (size_t)pl.W * n;
-    if (max_entries >= (1ull << 32)) {
-        set_last_error("msm: W*n must be < 2^32 (shard the MSM by point range)");
+    const unsigned c = lv.c;
+    const unsigned W = (255 + c - 1) / c; // W*c >= 255: the top window absorbs the last carry
+    const unsigned S = lv.L == 1 ? W : lv.D / c;
+    const uint32_t B = 1u << (c - 1);
+    const size_t G = (size_t)S * B;
+    const size_t max_entries = (size_t)W * n;
+    if (max_entries >= (1ull << 32) || ((size_t)(lv.L - 1) * lv.stride + base + n) >= (1ull << 31)) {
+        set_last_error("msm: too many points for 32-bit schedule entries (shard the MSM by point range)");
         return BBG_ERR_ARG;
     }
     int rc;
-    if ((rc = ctx->msm_counts.reserve((pl.G + 1) * 4))) return rc;
-    if ((rc = ctx->msm_offsets.reserve((pl.G + 1) * 4))) return rc;
-    if ((rc = ctx->msm_cursors.reserve((pl.G + 1) * 4))) return rc;
+    if ((rc = ctx->msm_counts.reserve((G + 1) * 4 + 64))) return rc;
+    if ((rc = ctx->msm_offsets.reserve((G + 1) * 4))) return rc;
+    if ((rc = ctx->msm_cursors.reserve((G + 1) * 4))) return rc;
     if ((rc = ctx->msm_sorted.reserve(max_entries * 4))) return rc;
-    if ((rc = ctx->msm_buckets.reserve(pl.G * sizeof(xyzz_t)))) return rc;
+    if ((rc = ctx->msm_buckets.reserve(G * sizeof(xyzz_t)))) return rc;
     uint32_t* counts = (uint32_t*)ctx->msm_counts.p;
     uint32_t* offsets = (uint32_t*)ctx->msm_offsets.p;
     uint32_t* cursors = (uint32_t*)ctx->msm_cursors.p;
     uint32_t* sorted = (uint32_t*)ctx->msm_sorted.p;
     xyzz_t* buckets = (xyzz_t*)ctx->msm_buckets.p;
+    uint32_t* pending = counts + G + 1; // 15 merge-level counters behind the histogram (zeroed with it)
 
-    BBG_CUDA(cudaMemsetAsync(counts, 0, (pl.G + 1) * 4, st));
-    BBG_CUDA(cudaMemsetAsync(buckets, 0, pl.G * sizeof(xyzz_t), st)); // all-zero XYZZ = infinity
+    pr.mark(st, PH_MSM_DIGITS);
+    BBG_CUDA(cudaMemsetAsync(counts, 0, (G + 1) * 4 + 64, st));
+    BBG_CUDA(cudaMemsetAsync(buckets, 0, G * sizeof(xyzz_t), st)); // all-zero XYZZ = infinity
 
+    DigitParams dp;
+    dp.n = (uint32_t)n;
+    dp.c = c;
+    dp.W = W;
+    dp.S = S;
+    dp.B = B;
+    dp.level_stride = (uint32_t)lv.stride;
+    dp.base = (uint32_t)base;
     const unsigned dig_blocks = div_up(n, 256);
-    k_msm_digits<false><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, (uint32_t)n, pl.c, pl.W, counts, nullptr);
+    k_msm_digits<false><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, counts, nullptr);
     ctx->launches += 1;
-    if ((rc = exclusive_scan(ctx, counts, pl.G, offsets, cursors, st))) return rc;
-    k_msm_digits<true><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, (uint32_t)n, pl.c, pl.W, cursors, sorted);
+    pr.mark(st, PH_MSM_SCAN);
+    if ((rc = exclusive_scan(ctx, counts, G, offsets, cursors, st))) return rc;
+    pr.mark(st, PH_MSM_SCATTER);
+    k_msm_digits<true><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, cursors, sorted);
     ctx->launches += 1;
 
     // chunking: equal work per thread; about two waves of resident threads, chunk >= 16 entries.
@@ -565,58 +778,68 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     size_t chunk = (max_entries + 2 * resident - 1) / (2 * resident);
     if (chunk < 16) chunk = 16;
     const size_t num_chunks = (max_entries + chunk - 1) / chunk;
-    if ((rc = ctx->msm_partials.reserve(2 * num_chunks * sizeof(Partial)))) return rc;
-    Partial* heads = (Partial*)ctx->msm_partials.p;
-    Partial* tails = heads + num_chunks;
-    // chunks past the real total never run their body: mark every partial "none" first
-    BBG_CUDA(cudaMemsetAsync(heads, 0xff, 2 * num_chunks * sizeof(Partial), st));
-
-    // the real total lives in offsets[G]; the kernel reads it from there (no host round trip)
-    k_msm_accumulate<<<div_up(num_chunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
-        sorted, offsets, (uint32_t)pl.G, (uint32_t)chunk, (const affine_t*)d_points, (uint32_t)point_stride, buckets,
-        heads, tails);
-    k_msm_fixup<<<div_up(num_chunks, 128), 128, 0, st>>>((uint32_t)num_chunks, heads, tails, buckets);
-    ctx->launches += 2;
-
-    // bucket reduction hierarchy
-    size_t level_elems = 0;
+    // slot arrays of all merge levels, back to back
+    size_t slots_total = 2 * num_chunks;
     {
-        uint32_t m = pl.B;
-        while (m > 1) {
-            uint32_t ell = m >= 16 ? 16 : m;
-            m /= ell;
-            level_elems += (size_t)m * pl.W;
+        size_t n_in = 2 * num_chunks;
+        for (unsigned level = 0; level < 14; ++level) {
+            const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
+            slots_total += 2 * workers;
+            if (workers == 1) break;
+            n_in = 2 * workers;
         }
-        if (pl.B == 1) level_elems = pl.W;
     }
-    if ((rc = ctx->msm_reduce.reserve(2 * (level_elems + pl.W) * sizeof(xyzz_t)))) return rc;
-    xyzz_t* pool = (xyzz_t*)ctx->msm_reduce.p;
-    const xyzz_t* r_in = buckets;
-    const xyzz_t* c_in = nullptr;
-    uint32_t m = pl.B, log_scale = 0;
-    if (m == 1) {
-        // c == 1 never happens (c >= 2), kept for completeness
-        set_last_error("msm: unsupported window");
-        return BBG_ERR_ARG;
-    }
-    while (m > 1) {
-        uint32_t ell = m >= 16 ? 16 : m;
-        uint32_t m_out = m / ell;
-        xyzz_t* r_out = pool;
-        xyzz_t* c_out = pool + (size_t)m_out * pl.W;
-        pool += 2 * (size_t)m_out * pl.W;
-        unsigned threads = m_out * pl.W;
-        k_msm_reduce_level<<<div_up(threads, 128), 128, 0, st>>>(r_in, c_in, m, ell, log_scale, pl.W, r_out, c_out);
-        ctx->launches += 1;
-        r_in = r_out;
-        c_in = c_out;
-        unsigned lg = 0;
-        while ((1u << lg) < ell) ++lg;
-        log_scale += lg;
-        m = m_out;
-    }
-    k_msm_combine<<<1, 32, 0, st>>>(r_in, c_in, pl.W, pl.c, (jac_t*)d_out);
+    if ((rc = ctx->msm_partials.reserve(slots_total * sizeof(Slot)))) return rc;
+    Slot* slots = (Slot*)ctx->msm_partials.p;
+
+    pr.mark(st, PH_MSM_ACCUMULATE);
+    k_msm_accumulate<<<div_up(num_chunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
+        sorted, offsets, (uint32_t)G, (uint32_t)chunk, (uint32_t)num_chunks, (const affine_t*)d_points, (uint32_t)point_stride,
+        buckets, slots, pending);
     ctx->launches += 1;
+    pr.mark(st, PH_MSM_FIXUP);
+    {
+        size_t n_in = 2 * num_chunks;
+        Slot* in = slots;
+        unsigned level = 0;
+        while (level < 14) {
+            const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
+            Slot* out = in + n_in;
+            k_msm_merge<<<div_up(workers, 128), 128, 0, st>>>(in, (uint32_t)n_in, (uint32_t)workers, pending + level, buckets, out,
+                                                             pending + level + 1);
+            ctx->launches += 1;
+            ++level;
+            if (workers == 1) break;
+            in = out;
+            n_in = 2 * workers;
+        }
+    }
+
+    // bucket reduction
+    pr.mark(st, PH_MSM_REDUCE);
+    uint32_t ell = 16;
+    while (ell > 1 && (G / ell) < 8192) ell >>= 1; // keep at least ~8K workers in flight
+    if (ell > B) ell = B;
+    const uint32_t segs = B / ell;
+    const uint32_t workers = segs * S;
+    const uint32_t parts = std::min<uint32_t>(64, std::max<uint32_t>(1, segs / 64));
+    if ((rc = ctx->msm_reduce.reserve(((size_t)workers + (size_t)S * parts + S) * sizeof(xyzz_t)))) return rc;
+    xyzz_t* seg_out = (xyzz_t*)ctx->msm_reduce.p;
+    xyzz_t* part_out = seg_out + workers;
+    xyzz_t* set_out = part_out + (size_t)S * parts;
+    k_msm_segments<<<div_up(workers, 128), 128, 0, st>>>(buckets, B, ell, workers, seg_out);
+    k_msm_tree_sum<<<dim3(parts, S), TREE_THREADS, 0, st>>>(seg_out, segs, part_out);
+    ctx->launches += 2;
+    const xyzz_t* sums = part_out;
+    if (parts > 1) {
+        k_msm_tree_sum<<<dim3(1, S), TREE_THREADS, 0, st>>>(part_out, parts, set_out);
+        ctx->launches += 1;
+        sums = set_out;
+    }
+    pr.mark(st, PH_MSM_COMBINE);
+    k_msm_finish<<<1, 32, 0, st>>>(sums, S, c, (jac_t*)d_out);
+    ctx->launches += 1;
+    pr.mark(st, -1);
     BBG_CUDA(cudaGetLastError());
     return BBG_OK;
 }

@@ -483,6 +483,9 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
     }
 
     int rc;
+    Profiler& pr = ctx->prof;
+    pr.begin();
+    pr.mark(st, PH_NTT_TABLES);
     if ((rc = ensure_stage_tables(ctx, st))) return rc;
     const fr* tw_big = nullptr;
     if ((rc = ensure_big_table(ctx, log_n, &tw_big, st))) return rc;
@@ -582,10 +585,12 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         const uint64_t num_tiles = N >> (gb[p] + 3);
         const unsigned tiles_per_cta = NTT_THREADS >> gb[p];
         const unsigned blocks = (unsigned)((num_tiles + tiles_per_cta - 1) / tiles_per_cta);
+        pr.mark(st, PH_NTT_PASS0 + (int)p);
         k_ntt_pass<<<blocks, NTT_THREADS, NTT_SMEM_BYTES, st>>>(pp);
         ctx->launches += 1;
         above += gb[p];
     }
+    pr.mark(st, -1);
     BBG_CUDA(cudaGetLastError());
     return BBG_OK;
 }

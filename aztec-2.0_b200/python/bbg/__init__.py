@@ -1,0 +1,369 @@
+"""bbg -- thin ctypes binding over libbbg.so (include/bbg.h), used by the tests, smoke() and bench.py.
+
+The product is the C-ABI library (hand-written sm_100a CUDA behind barretenberg's call signatures);
+this module only marshals numpy arrays (host pointers) and torch CUDA tensors (device pointers) into
+it.  Names mirror barretenberg's: ``Pippenger`` (bb/ecc/curves/bn254/scalar_multiplication/pippenger.hpp:35-52),
+``pippenger`` / ``pippenger_unsafe`` (scalar_multiplication.hpp:139-148), ``fft`` / ``ifft`` / ``coset_fft`` /
+``coset_ifft`` / ``*_with_constant`` / ``coset_fft_with_generator_shift`` (bb/polynomials/polynomial_arithmetic.hpp:23-39),
+``g1_sum`` (c_bind.cpp:40-45).  Errors raise ``BbgError`` carrying the library's message, like the
+reference's throw_or_abort.
+
+There is NO CPU fallback: if libbbg.so is missing the import fails; without a CUDA device every
+compute call raises BbgError(BBG_ERR_NO_DEVICE).
+
+Layouts (numpy uint64): fr/fq (..., 4); g1 affine (..., 8); g1 Jacobian (..., 12) -- barretenberg's.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "libbbg.so"))
+
+OK, ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_SRS, ERR_IO = range(6)
+(FFT, IFFT, COSET_FFT, COSET_IFFT, FFT_WITH_CONSTANT, IFFT_WITH_CONSTANT, COSET_FFT_WITH_CONSTANT,
+ COSET_FFT_WITH_GENERATOR_SHIFT) = range(8)
+
+EXPORTS = [
+    "bbg_profile", "bbg_profile_read", "bbg_init", "bbg_shutdown", "bbg_last_error", "bbg_device_count", "bbg_kernel_launches", "bbg_last_device_ms",
+    "bbg_malloc", "bbg_free", "bbg_new_pippenger", "bbg_new_pippenger_from_path", "bbg_new_pippenger_from_table",
+    "bbg_new_pippenger_from_points", "bbg_delete_pippenger", "bbg_pippenger_num_points", "bbg_pippenger_get_point_table",
+    "bbg_pippenger_device_points", "bbg_pippenger_unsafe", "bbg_pippenger_unsafe_dev", "bbg_pippenger", "bbg_msm_points",
+    "bbg_msm_points_dev", "bbg_generate_pippenger_point_table", "bbg_g1_sum", "bbg_g1_sum_dev", "bbg_read_transcript_g1",
+    "bbg_read_g1_elements_from_buffer", "bbg_ntt", "bbg_ntt_dev", "bbg_coset_fft_ext", "bbg_coset_fft_ext_dev",
+    "bbg_new_evaluation_domain", "bbg_delete_evaluation_domain", "bbg_ifft", "bbg_coset_fft_with_generator_shift",
+    "bbg_domain_constants", "bbg_field_op", "bbg_g1_op",
+]
+
+
+class BbgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libbbg error %d: %s" % (code, msg))
+        self.code = code
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("libbbg.so not built (run `make -C aztec-2.0_b200/csrc` or __graft_entry__.build()); "
+                      "there is no CPU fallback")
+lib = ctypes.CDLL(LIB_PATH)
+
+_vp, _sz, _int = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+lib.bbg_last_error.restype = ctypes.c_char_p
+lib.bbg_kernel_launches.restype = ctypes.c_uint64
+lib.bbg_last_device_ms.restype = ctypes.c_double
+lib.bbg_malloc.restype = _vp
+lib.bbg_malloc.argtypes = [_sz]
+lib.bbg_free.argtypes = [_vp]
+for _n in ("bbg_new_pippenger", "bbg_new_pippenger_from_table", "bbg_new_pippenger_from_points"):
+    getattr(lib, _n).restype = _vp
+    getattr(lib, _n).argtypes = [_vp, _sz]
+lib.bbg_new_pippenger_from_path.restype = _vp
+lib.bbg_new_pippenger_from_path.argtypes = [ctypes.c_char_p, _sz]
+lib.bbg_delete_pippenger.argtypes = [_vp]
+lib.bbg_pippenger_num_points.restype = _sz
+lib.bbg_pippenger_num_points.argtypes = [_vp]
+lib.bbg_pippenger_get_point_table.argtypes = [_vp, _vp]
+lib.bbg_pippenger_device_points.restype = _vp
+lib.bbg_pippenger_device_points.argtypes = [_vp]
+lib.bbg_pippenger_unsafe.argtypes = [_vp, _vp, _sz, _sz, _vp]
+lib.bbg_pippenger_unsafe_dev.argtypes = [_vp, _vp, _sz, _sz, _vp, _vp]
+lib.bbg_pippenger.argtypes = [_vp, _vp, _sz, _int, _vp]
+lib.bbg_msm_points.argtypes = [_vp, _vp, _sz, _vp]
+lib.bbg_msm_points_dev.argtypes = [_vp, _vp, _sz, _sz, _vp, _vp]
+lib.bbg_generate_pippenger_point_table.argtypes = [_vp, _vp, _sz]
+lib.bbg_g1_sum.argtypes = [_vp, _sz, _vp]
+lib.bbg_g1_sum_dev.argtypes = [_vp, _sz, _vp, _vp]
+lib.bbg_read_transcript_g1.argtypes = [_vp, _sz, ctypes.c_char_p]
+lib.bbg_read_g1_elements_from_buffer.argtypes = [_vp, _vp, _sz]
+lib.bbg_ntt.argtypes = [_vp, _sz, _int, _sz, _vp]
+lib.bbg_ntt_dev.argtypes = [_vp, _sz, _int, _sz, _vp, _vp]
+lib.bbg_coset_fft_ext.argtypes = [_vp, _sz, _sz]
+lib.bbg_coset_fft_ext_dev.argtypes = [_vp, _sz, _sz, _vp]
+lib.bbg_new_evaluation_domain.restype = _vp
+lib.bbg_new_evaluation_domain.argtypes = [_sz]
+lib.bbg_delete_evaluation_domain.argtypes = [_vp]
+lib.bbg_ifft.argtypes = [_vp, _vp]
+lib.bbg_coset_fft_with_generator_shift.argtypes = [_vp, _vp, _vp]
+lib.bbg_domain_constants.argtypes = [_sz, _vp]
+lib.bbg_field_op.argtypes = [_int, _int, _vp, _vp, _vp, _sz]
+lib.bbg_g1_op.argtypes = [_int, _vp, _vp, _vp, _sz]
+lib.bbg_init.argtypes = [_int]
+lib.bbg_profile.argtypes = [_int]
+lib.bbg_profile_read.argtypes = [_vp, _int]
+NUM_PHASES = 12
+PHASE_NAMES = ["msm_digits", "msm_scan", "msm_scatter", "msm_accumulate", "msm_fixup", "msm_reduce", "msm_combine",
+               "ntt_tables", "ntt_pass0", "ntt_pass1", "ntt_pass2", "ntt_pass3"]
+
+
+def _check(rc):
+    if rc != OK:
+        raise BbgError(rc, (lib.bbg_last_error() or b"").decode(errors="replace"))
+
+
+def _np(a, width=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if width is not None:
+        a = a.reshape(-1, width)
+    return a
+
+
+def _ptr(a):
+    """host pointer of a numpy array, or device pointer of a torch CUDA tensor"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    return stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+
+
+def init(device=-1):
+    _check(lib.bbg_init(device))
+
+
+def shutdown():
+    lib.bbg_shutdown()
+
+
+def device_count():
+    return int(lib.bbg_device_count())
+
+
+def kernel_launches():
+    return int(lib.bbg_kernel_launches())
+
+
+def last_device_ms():
+    return float(lib.bbg_last_device_ms())
+
+
+def profile(enable):
+    _check(lib.bbg_profile(1 if enable else 0))
+
+
+def profile_read():
+    """{phase name: milliseconds} of the last compute call (device time, CUDA events)."""
+    ms = (ctypes.c_double * NUM_PHASES)()
+    _check(lib.bbg_profile_read(ctypes.cast(ms, ctypes.c_void_p), NUM_PHASES))
+    return {PHASE_NAMES[i]: float(ms[i]) for i in range(NUM_PHASES)}
+
+
+def pinned_empty(shape, dtype=np.uint64):
+    """numpy array over page-locked host memory from bbg_malloc (bbmalloc, c_bind.cpp:11-19)."""
+    shape = (shape,) if isinstance(shape, (int, np.integer)) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    p = lib.bbg_malloc(max(nbytes, 1))
+    if not p:
+        raise BbgError(ERR_CUDA, (lib.bbg_last_error() or b"").decode())
+    buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    _PINNED[arr.ctypes.data] = p
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr):
+    p = _PINNED.pop(arr.ctypes.data, None)
+    if p:
+        lib.bbg_free(p)
+
+
+class Pippenger:
+    """bb/.../pippenger.hpp:35-52: owns the SRS (here: resident in HBM as n affine points)."""
+
+    def __init__(self, handle, keep=None):
+        if not handle:
+            raise BbgError(ERR_SRS, (lib.bbg_last_error() or b"").decode(errors="replace"))
+        self.h = handle
+        self._keep = keep
+
+    @classmethod
+    def from_path(cls, srs_dir, num_points):
+        return cls(lib.bbg_new_pippenger_from_path(str(srs_dir).encode(), num_points))
+
+    @classmethod
+    def from_raw(cls, raw_points, num_points):
+        raw = np.ascontiguousarray(np.frombuffer(raw_points, dtype=np.uint8) if not isinstance(raw_points, np.ndarray) else raw_points)
+        return cls(lib.bbg_new_pippenger(raw.ctypes.data, num_points))
+
+    @classmethod
+    def from_table(cls, table2n, num_points):
+        t = _np(table2n, 8)
+        return cls(lib.bbg_new_pippenger_from_table(t.ctypes.data, num_points), keep=t)
+
+    @classmethod
+    def from_points(cls, points, num_points=None):
+        p = _np(points, 8)
+        n = p.shape[0] if num_points is None else num_points
+        return cls(lib.bbg_new_pippenger_from_points(p.ctypes.data, n))
+
+    def get_num_points(self):
+        return int(lib.bbg_pippenger_num_points(self.h))
+
+    def get_point_table(self):
+        out = np.zeros((2 * self.get_num_points(), 8), dtype=np.uint64)
+        _check(lib.bbg_pippenger_get_point_table(self.h, out.ctypes.data))
+        return out
+
+    def device_points(self):
+        return int(lib.bbg_pippenger_device_points(self.h) or 0)
+
+    def pippenger_unsafe(self, scalars, from_=0, range_=None, stream=None):
+        """MSM over monomials [from, from+range).  numpy scalars -> numpy Jacobian (12,);
+        torch CUDA scalars -> torch CUDA uint8[96] (asynchronous on `stream`)."""
+        if isinstance(scalars, np.ndarray) or not hasattr(scalars, "data_ptr"):
+            s = _np(scalars, 4)
+            n = s.shape[0] if range_ is None else range_
+            out = np.zeros(12, dtype=np.uint64)
+            _check(lib.bbg_pippenger_unsafe(self.h, s.ctypes.data, from_, n, out.ctypes.data))
+            return out
+        import torch
+        n = scalars.numel() * scalars.element_size() // 32 if range_ is None else range_
+        out = torch.empty(96, dtype=torch.uint8, device=scalars.device)
+        _check(lib.bbg_pippenger_unsafe_dev(self.h, scalars.data_ptr(), from_, n, out.data_ptr(), _stream_ptr(stream)))
+        return out
+
+    def close(self):
+        if self.h:
+            lib.bbg_delete_pippenger(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pippenger(scalars, points_table2n, num_points, handle_edge_cases=True):
+    s, t = _np(scalars, 4), _np(points_table2n, 8)
+    out = np.zeros(12, dtype=np.uint64)
+    _check(lib.bbg_pippenger(s.ctypes.data if num_points else None, t.ctypes.data if num_points else None, num_points,
+                             1 if handle_edge_cases else 0, out.ctypes.data))
+    return out
+
+
+def pippenger_unsafe(scalars, points_table2n, num_points):
+    return pippenger(scalars, points_table2n, num_points, handle_edge_cases=False)
+
+
+def msm_points(scalars, points, num_points=None):
+    s, p = _np(scalars, 4), _np(points, 8)
+    n = s.shape[0] if num_points is None else num_points
+    out = np.zeros(12, dtype=np.uint64)
+    _check(lib.bbg_msm_points(s.ctypes.data if n else None, p.ctypes.data if n else None, n, out.ctypes.data))
+    return out
+
+
+def generate_pippenger_point_table(points):
+    p = _np(points, 8)
+    out = np.zeros((2 * p.shape[0], 8), dtype=np.uint64)
+    _check(lib.bbg_generate_pippenger_point_table(p.ctypes.data, out.ctypes.data, p.shape[0]))
+    return out
+
+
+def g1_sum(elements):
+    e = _np(elements, 12)
+    out = np.zeros(12, dtype=np.uint64)
+    _check(lib.bbg_g1_sum(e.ctypes.data, e.shape[0], out.ctypes.data))
+    return out
+
+
+def read_transcript_g1(degree, srs_dir):
+    out = np.zeros((degree, 8), dtype=np.uint64)
+    _check(lib.bbg_read_transcript_g1(out.ctypes.data, degree, str(srs_dir).encode()))
+    return out
+
+
+def read_g1_elements_from_buffer(raw):
+    raw = np.ascontiguousarray(np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw)
+    n = raw.size // 64
+    out = np.zeros((n, 8), dtype=np.uint64)
+    _check(lib.bbg_read_g1_elements_from_buffer(out.ctypes.data, raw.ctypes.data, n * 64))
+    return out
+
+
+def ntt(coeffs, kind, generator_size=0, constant=None, n=None, stream=None):
+    """In place.  numpy array -> host entry point (returns the same array); torch CUDA tensor -> _dev."""
+    k = None if constant is None else _np(constant, 4)
+    kp = None if k is None else k.ctypes.data
+    if isinstance(coeffs, np.ndarray):
+        assert coeffs.dtype == np.uint64 and coeffs.flags["C_CONTIGUOUS"]
+        size = coeffs.size // 4 if n is None else n
+        _check(lib.bbg_ntt(coeffs.ctypes.data, size, kind, generator_size, kp))
+        return coeffs
+    size = coeffs.numel() * coeffs.element_size() // 32 if n is None else n
+    _check(lib.bbg_ntt_dev(coeffs.data_ptr(), size, kind, generator_size, kp, _stream_ptr(stream)))
+    return coeffs
+
+
+def fft(c, **kw):
+    return ntt(c, FFT, **kw)
+
+
+def ifft(c, **kw):
+    return ntt(c, IFFT, **kw)
+
+
+def coset_fft(c, generator_size=0, **kw):
+    return ntt(c, COSET_FFT, generator_size=generator_size, **kw)
+
+
+def coset_ifft(c, **kw):
+    return ntt(c, COSET_IFFT, **kw)
+
+
+def fft_with_constant(c, value, **kw):
+    return ntt(c, FFT_WITH_CONSTANT, constant=value, **kw)
+
+
+def ifft_with_constant(c, value, **kw):
+    return ntt(c, IFFT_WITH_CONSTANT, constant=value, **kw)
+
+
+def coset_fft_with_constant(c, value, generator_size=0, **kw):
+    return ntt(c, COSET_FFT_WITH_CONSTANT, generator_size=generator_size, constant=value, **kw)
+
+
+def coset_fft_with_generator_shift(c, value, generator_size=0, **kw):
+    return ntt(c, COSET_FFT_WITH_GENERATOR_SHIFT, generator_size=generator_size, constant=value, **kw)
+
+
+def coset_fft_ext(coeffs, n, domain_extension, stream=None):
+    """coset_fft(coeffs, small_domain, large_domain, ext): coeffs holds ext*n elements, first n = input."""
+    if isinstance(coeffs, np.ndarray):
+        _check(lib.bbg_coset_fft_ext(coeffs.ctypes.data, n, domain_extension))
+    else:
+        _check(lib.bbg_coset_fft_ext_dev(coeffs.data_ptr(), n, domain_extension, _stream_ptr(stream)))
+    return coeffs
+
+
+def domain_constants(n):
+    out = np.zeros((6, 4), dtype=np.uint64)
+    _check(lib.bbg_domain_constants(n, out.ctypes.data))
+    return out
+
+
+def field_op(field, op, a, b=None):
+    a = _np(a, 4)
+    bb = None if b is None else _np(b, 4)
+    out = np.zeros_like(a)
+    _check(lib.bbg_field_op(field, op, a.ctypes.data, None if bb is None else bb.ctypes.data, out.ctypes.data, a.shape[0]))
+    return out
+
+
+def g1_op(op, a, b=None):
+    a = _np(a, 12)
+    bb = None if b is None else _np(b, 8 if op == 0 else 12)
+    out = np.zeros_like(a)
+    _check(lib.bbg_g1_op(op, a.ctypes.data, None if bb is None else bb.ctypes.data, out.ctypes.data, a.shape[0]))
+    return out

@@ -20,6 +20,11 @@
 extern "C" {
 #endif
 
+/* every entry point below has default visibility; everything else in libbbg.so is hidden */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
 #define BBG_OK 0
 #define BBG_ERR_CUDA 1
 #define BBG_ERR_ARG 2
@@ -34,6 +39,14 @@ const char* bbg_last_error(void);
 int bbg_device_count(void);
 uint64_t bbg_kernel_launches(void);    /* kernels this library has launched so far (bench.py reports it) */
 double bbg_last_device_ms(void);       /* CUDA-event time of the kernels of the last host-pointer call */
+
+/* Per-phase device timing of the LAST compute call (CUDA events on the launching stream; measurement aid
+ * for bench.py, no reference counterpart).  Phases: 0 msm digits+histogram, 1 scan, 2 scatter, 3 bucket
+ * accumulate, 4 fixup, 5 bucket reduce, 6 window combine, 7 ntt tables, 8..11 ntt pass 0..3.
+ * bbg_profile_read synchronises on the recorded events and fills ms[0..n) (0 for phases that did not run). */
+#define BBG_NUM_PHASES 12
+int bbg_profile(int enable);
+int bbg_profile_read(double* ms, int n);
 
 /* bb/ecc/curves/bn254/scalar_multiplication/c_bind.cpp:11-19  bbmalloc / bbfree.
  * Returns page-locked host memory so the host-pointer entry points copy at full PCIe rate. */
@@ -118,6 +131,10 @@ int bbg_domain_constants(size_t n, void* out6);
 int bbg_field_op(int field, int op, const void* a, const void* b, void* out, size_t n);
 /* g1 probe: op 0 mixed add (jac, affine) 1 add (jac, jac) 2 dbl (jac); inputs/outputs 96-byte Jacobian */
 int bbg_g1_op(int op, const void* a, const void* b, void* out, size_t n);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 
 #ifdef __cplusplus
 }
