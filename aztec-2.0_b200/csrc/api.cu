@@ -92,6 +92,7 @@ struct PippengerObj {
     const void* host_table = nullptr; // adopted 2n host table (for pointer recognition), may be null
 };
 static std::vector<PippengerObj*> g_pippengers;
+static int g_auto_adopt = -1; // -1: read BBG_AUTO_ADOPT on first use
 
 static int upload_even_entries(Context* ctx, const void* table2n, size_t n, affine_t* d_points)
 {
@@ -233,6 +234,35 @@ __global__ void k_g1_op(int op, const jac_t* a, const void* b, jac_t* out, size_
     fe_store(&out[i].x, r.x);
     fe_store(&out[i].y, r.y);
     fe_store(&out[i].z, r.z);
+}
+
+template <class F> __global__ void __launch_bounds__(256) k_bench_mul(Fe<F>* out, int iters)
+{
+    Fe<F> x, y;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x.l[i] = threadIdx.x * 7 + i + 1;
+        y.l[i] = blockIdx.x + i * 3 + 5;
+    }
+    x.l[7] &= 0x0fffffff;
+    y.l[7] &= 0x0fffffff;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        x = fe_mul(x, y);
+        y = fe_mul(y, x);
+    }
+    if (x.l[0] == 0x12345678 && y.l[3] == 0x9abcdef0) fe_store(out + threadIdx.x, x); // never true in practice; keeps the chain live
+}
+__global__ void __launch_bounds__(128) k_g1_add_affine(const affine_t* __restrict__ in, affine_t* __restrict__ out, size_t n, affine_t q)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t p = affine_load(in + i);
+    xyzz_t acc = xyzz_from_affine(p);
+    if (!affine_is_inf(q)) xyzz_madd(acc, q);
+    affine_t r = xyzz_to_affine(acc);
+    fe_store(&out[i].x, r.x);
+    fe_store(&out[i].y, r.y);
 }
 
 // NTT kind -> prologue/epilogue scalings (bb/polynomials/polynomial_arithmetic.cpp:374-484)
@@ -489,6 +519,39 @@ void* bbg_new_pippenger_from_points(const void* points, size_t num_points)
     return finish_obj(ctx, o, rc);
 }
 
+void* bbg_new_pippenger_from_device_points(const void* d_points, size_t num_points)
+{
+    Context* ctx = nullptr;
+    if (get_context(&ctx)) return nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PippengerObj* o = new_obj(ctx, num_points);
+    if (!o) return nullptr;
+    int rc = BBG_OK;
+    if (num_points && cudaMemcpyAsync(o->d_points, d_points, num_points * 64, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
+        set_last_error("D2D copy of points failed");
+        rc = BBG_ERR_CUDA;
+    }
+    return finish_obj(ctx, o, rc);
+}
+
+int bbg_pippenger_bind_host_table(void* pippenger, const void* table2n)
+{
+    GET_CTX();
+    PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
+    if (!o) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    o->host_table = table2n;
+    return BBG_OK;
+}
+
+int bbg_set_auto_adopt(int enable)
+{
+    g_auto_adopt = enable ? 1 : 0;
+    return BBG_OK;
+}
+
 void bbg_delete_pippenger(void* pippenger)
 {
     PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
@@ -589,6 +652,19 @@ int bbg_pippenger(const void* scalars, const void* points_table2n, size_t num_po
         }
     }
     int rc;
+    if (g_auto_adopt < 0) {
+        const char* e = getenv("BBG_AUTO_ADOPT");
+        g_auto_adopt = (e && *e && *e != '0') ? 1 : 0;
+    }
+    if (g_auto_adopt == 1 && num_points >= 4096) {
+        // first sight of an (immutable) SRS table: make it resident, with its fixed-base levels
+        PippengerObj* o = new_obj(ctx, num_points);
+        if (!o) return BBG_ERR_CUDA;
+        o->host_table = points_table2n;
+        rc = upload_even_entries(ctx, points_table2n, num_points, o->d_points);
+        if (finish_obj(ctx, o, rc) == nullptr) return BBG_ERR_CUDA;
+        return msm_host_scalars(ctx, scalars, num_points, o->d_points, 1, o->lv, 0, result);
+    }
     if ((rc = ctx->msm_points.reserve(std::max<size_t>(num_points, 1) * 64))) return rc;
     if (num_points && (rc = upload_even_entries(ctx, points_table2n, num_points, (affine_t*)ctx->msm_points.p))) return rc;
     return msm_host_scalars(ctx, scalars, num_points, (const affine_t*)ctx->msm_points.p, 1, MsmLevels(), 0, result);
@@ -795,6 +871,54 @@ int bbg_domain_constants(size_t n, void* out6)
     c[4] = coset_generator();
     c[5] = hf::invert(c[4]);
     memcpy(out6, c, sizeof(c));
+    return BBG_OK;
+}
+
+// ---- measurement / synthetic-input utilities
+int bbg_bench_field_mul(int field, int iters, double* muls_per_second)
+{
+    GET_CTX();
+    if (!muls_per_second || iters <= 0) {
+        set_last_error("bad argument");
+        return BBG_ERR_ARG;
+    }
+    void* d_out = nullptr;
+    BBG_CUDA(cudaMalloc(&d_out, 256 * 32));
+    const int blocks = ctx->num_sms * 8;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) { // first repetition warms up
+        cudaEventRecord(ctx->ev_a, ctx->stream);
+        if (field == 0) {
+            k_bench_mul<FqParams><<<blocks, 256, 0, ctx->stream>>>((fq_t*)d_out, iters);
+        } else {
+            k_bench_mul<FrParams><<<blocks, 256, 0, ctx->stream>>>((fr_t*)d_out, iters);
+        }
+        ctx->launches += 1;
+        cudaEventRecord(ctx->ev_b, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            cudaFree(d_out);
+            set_last_error(cudaGetErrorString(e));
+            return BBG_ERR_CUDA;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d_out);
+    *muls_per_second = (double)blocks * 256.0 * 2.0 * iters / (best * 1e-3);
+    return BBG_OK;
+}
+
+int bbg_g1_add_affine_dev(const void* d_in, void* d_out, size_t n, const void* q_affine, void* stream)
+{
+    GET_CTX();
+    if (n == 0) return BBG_OK;
+    affine_t q;
+    memcpy(&q, q_affine, 64);
+    k_g1_add_affine<<<div_up(n, 128), 128, 0, (cudaStream_t)stream>>>((const affine_t*)d_in, (affine_t*)d_out, n, q);
+    ctx->launches += 1;
+    BBG_CUDA(cudaGetLastError());
     return BBG_OK;
 }
 

@@ -26,9 +26,9 @@ OK, ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_SRS, ERR_IO = range(6)
  COSET_FFT_WITH_GENERATOR_SHIFT) = range(8)
 
 EXPORTS = [
-    "bbg_profile", "bbg_profile_read", "bbg_init", "bbg_shutdown", "bbg_last_error", "bbg_device_count", "bbg_kernel_launches", "bbg_last_device_ms",
+    "bbg_pippenger_bind_host_table", "bbg_set_auto_adopt", "bbg_bench_field_mul", "bbg_g1_add_affine_dev", "bbg_profile", "bbg_profile_read", "bbg_init", "bbg_shutdown", "bbg_last_error", "bbg_device_count", "bbg_kernel_launches", "bbg_last_device_ms",
     "bbg_malloc", "bbg_free", "bbg_new_pippenger", "bbg_new_pippenger_from_path", "bbg_new_pippenger_from_table",
-    "bbg_new_pippenger_from_points", "bbg_delete_pippenger", "bbg_pippenger_num_points", "bbg_pippenger_get_point_table",
+    "bbg_new_pippenger_from_points", "bbg_new_pippenger_from_device_points", "bbg_delete_pippenger", "bbg_pippenger_num_points", "bbg_pippenger_get_point_table",
     "bbg_pippenger_device_points", "bbg_pippenger_unsafe", "bbg_pippenger_unsafe_dev", "bbg_pippenger", "bbg_msm_points",
     "bbg_msm_points_dev", "bbg_generate_pippenger_point_table", "bbg_g1_sum", "bbg_g1_sum_dev", "bbg_read_transcript_g1",
     "bbg_read_g1_elements_from_buffer", "bbg_ntt", "bbg_ntt_dev", "bbg_coset_fft_ext", "bbg_coset_fft_ext_dev",
@@ -55,7 +55,8 @@ lib.bbg_last_device_ms.restype = ctypes.c_double
 lib.bbg_malloc.restype = _vp
 lib.bbg_malloc.argtypes = [_sz]
 lib.bbg_free.argtypes = [_vp]
-for _n in ("bbg_new_pippenger", "bbg_new_pippenger_from_table", "bbg_new_pippenger_from_points"):
+for _n in ("bbg_new_pippenger", "bbg_new_pippenger_from_table", "bbg_new_pippenger_from_points",
+           "bbg_new_pippenger_from_device_points"):
     getattr(lib, _n).restype = _vp
     getattr(lib, _n).argtypes = [_vp, _sz]
 lib.bbg_new_pippenger_from_path.restype = _vp
@@ -91,6 +92,10 @@ lib.bbg_g1_op.argtypes = [_int, _vp, _vp, _vp, _sz]
 lib.bbg_init.argtypes = [_int]
 lib.bbg_profile.argtypes = [_int]
 lib.bbg_profile_read.argtypes = [_vp, _int]
+lib.bbg_pippenger_bind_host_table.argtypes = [_vp, _vp]
+lib.bbg_set_auto_adopt.argtypes = [_int]
+lib.bbg_bench_field_mul.argtypes = [_int, _int, _vp]
+lib.bbg_g1_add_affine_dev.argtypes = [_vp, _vp, _sz, _vp, _vp]
 NUM_PHASES = 12
 PHASE_NAMES = ["msm_digits", "msm_scan", "msm_scatter", "msm_accumulate", "msm_fixup", "msm_reduce", "msm_combine",
                "ntt_tables", "ntt_pass0", "ntt_pass1", "ntt_pass2", "ntt_pass3"]
@@ -155,6 +160,22 @@ def profile_read():
     return {PHASE_NAMES[i]: float(ms[i]) for i in range(NUM_PHASES)}
 
 
+def bench_field_mul(field=0, iters=2000):
+    """Sustained register-resident Montgomery multiplies per second over the whole GPU (integer-pipe roofline)."""
+    out = ctypes.c_double(0.0)
+    _check(lib.bbg_bench_field_mul(field, iters, ctypes.cast(ctypes.pointer(out), ctypes.c_void_p)))
+    return out.value
+
+
+def g1_add_affine(points_dev, q_affine, out_dev=None, stream=None):
+    """out[i] = affine(points[i] + q) on torch CUDA tensors holding 64-byte affine points (synthetic bases)."""
+    out_dev = points_dev if out_dev is None else out_dev
+    q = _np(q_affine, 8)
+    n = points_dev.numel() * points_dev.element_size() // 64
+    _check(lib.bbg_g1_add_affine_dev(points_dev.data_ptr(), out_dev.data_ptr(), n, q.ctypes.data, _stream_ptr(stream)))
+    return out_dev
+
+
 def pinned_empty(shape, dtype=np.uint64):
     """numpy array over page-locked host memory from bbg_malloc (bbmalloc, c_bind.cpp:11-19)."""
     shape = (shape,) if isinstance(shape, (int, np.integer)) else tuple(shape)
@@ -199,6 +220,16 @@ class Pippenger:
     def from_table(cls, table2n, num_points):
         t = _np(table2n, 8)
         return cls(lib.bbg_new_pippenger_from_table(t.ctypes.data, num_points), keep=t)
+
+    @classmethod
+    def from_device_points(cls, points_dev, num_points=None):
+        """points_dev: torch CUDA tensor of 64-byte affine points (copied device-to-device into the object)."""
+        import torch
+        n = points_dev.numel() * points_dev.element_size() // 64 if num_points is None else num_points
+        host = torch.empty(0)
+        del host
+        obj = cls(lib.bbg_new_pippenger_from_device_points(points_dev.data_ptr(), n))
+        return obj
 
     @classmethod
     def from_points(cls, points, num_points=None):

@@ -64,8 +64,18 @@ void* bbg_new_pippenger_from_path(const char* srs_dir, size_t num_points);
  * (what ProverReferenceString::get_monomials() returns, bb/plonk/reference_string/reference_string.hpp:24-38).
  * The host pointer is remembered so bbg_pippenger() can recognise it. */
 void* bbg_new_pippenger_from_table(const void* table2n, size_t num_points);
+/* Tell the library that `table2n` (host) holds this object's 2n interleaved table, so that bbg_pippenger() calls
+ * made with a pointer into it (ProverReferenceString::get_monomials(), pippenger.cpp:27-31 monomials_ + 2*from)
+ * run on the resident device copy instead of re-uploading the bases. */
+int bbg_pippenger_bind_host_table(void* pippenger, const void* table2n);
+/* When enabled (or BBG_AUTO_ADOPT=1 in the environment), bbg_pippenger() adopts an unknown table of >= 2^12 points on
+ * first sight as bbg_new_pippenger_from_table would -- valid only if the caller never changes that memory
+ * (true for a PLONK SRS); off by default. */
+int bbg_set_auto_adopt(int enable);
 /* Adopt a plain host array of num_points affine elements. */
 void* bbg_new_pippenger_from_points(const void* points, size_t num_points);
+/* Same from device memory (device-to-device copy; used for synthetic bases built on the GPU). */
+void* bbg_new_pippenger_from_device_points(const void* d_points, size_t num_points);
 /* c_bind.cpp:31-34 delete_pippenger */
 void bbg_delete_pippenger(void* pippenger);
 /* pippenger.hpp:47-49 get_num_points / get_point_table (copies the 2n interleaved table to host memory) */
@@ -131,6 +141,14 @@ int bbg_domain_constants(size_t n, void* out6);
 int bbg_field_op(int field, int op, const void* a, const void* b, void* out, size_t n);
 /* g1 probe: op 0 mixed add (jac, affine) 1 add (jac, jac) 2 dbl (jac); inputs/outputs 96-byte Jacobian */
 int bbg_g1_op(int op, const void* a, const void* b, void* out, size_t n);
+
+/* ---- measurement / synthetic-input utilities (no reference counterpart) ------------------------ */
+/* Integer-pipe roofline: back-to-back register-resident Montgomery multiplies (field 0 fq, 1 fr) on every SM;
+ * writes the sustained rate in multiplies per second.  bench.py reports MSM/NTT arithmetic against it. */
+int bbg_bench_field_mul(int field, int iters, double* muls_per_second);
+/* out[i] = affine(in[i] + q): distinct synthetic bases beyond the 2^20-point SRS (Q_j = Q_{j-1} + D).
+ * in/out: n affine points in device memory (may alias); q: one affine point in host memory. */
+int bbg_g1_add_affine_dev(const void* d_in, void* d_out, size_t n, const void* q_affine, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
