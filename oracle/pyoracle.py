@@ -21,6 +21,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libbn254_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libbbref.so")
+REF_GPU_SO = os.path.join(HERE, "_ref", "libbbref_gpu.so")  # same reference objects, hot path -> bbg_shim.cpp -> libbbg.so
 REF_SRS_DIR = os.path.join(HERE, "_ref", "srs_db")
 
 FQ, FR = 0, 1
@@ -257,8 +258,8 @@ class Ref:
     def available():
         return os.path.exists(REF_SO)
 
-    def __init__(self):
-        self.lib = L = ctypes.CDLL(REF_SO)
+    def __init__(self, path=None):
+        self.lib = L = ctypes.CDLL(path or REF_SO)
         L.ref_point_table_size.restype = ctypes.c_size_t
         L.ref_new_domain.restype = ctypes.c_void_p
         L.ref_new_runtime_state.restype = ctypes.c_void_p
@@ -396,6 +397,30 @@ class Ref:
         rc = self.lib.ref_pippenger(_p(scalars), _p(table), ctypes.c_size_t(n), state, 1 if unsafe else 0, _p(out))
         if rc != 0:
             raise RuntimeError("reference pippenger threw")
+        return out
+
+    # Pippenger class (pippenger.hpp:35-52)
+    def new_pippenger(self, srs_dir, num_points):
+        self.lib.ref_new_pippenger_from_path.restype = ctypes.c_void_p
+        h = self.lib.ref_new_pippenger_from_path(srs_dir.encode(), ctypes.c_size_t(num_points))
+        if not h:
+            raise RuntimeError("Pippenger constructor threw")
+        return ctypes.c_void_p(h)
+
+    def delete_pippenger(self, h):
+        self.lib.ref_delete_pippenger(h)
+
+    def pippenger_table(self, h, num_points):
+        out = aligned_empty((2 * num_points, 8))
+        self.lib.ref_pippenger_copy_table(h, _p(out))
+        return out
+
+    def pippenger_class_unsafe(self, h, scalars, from_, range_):
+        scalars = aligned_copy(scalars)
+        out = aligned_empty(12)
+        rc = self.lib.ref_pippenger_class_unsafe(h, _p(scalars), ctypes.c_size_t(from_), ctypes.c_size_t(range_), _p(out))
+        if rc != 0:
+            raise RuntimeError("Pippenger::pippenger_unsafe threw")
         return out
 
     def naive_msm(self, scalars, points, n=None, stride=2):

@@ -252,6 +252,34 @@ void ref_naive_msm(const void* scalars, const void* affine_points, size_t n, siz
     *reinterpret_cast<g1::element*>(out_jac) = acc;
 }
 
+// ---- Pippenger class (pippenger.hpp:35-52): SRS owner + MSM over a point range
+void* ref_new_pippenger_from_path(const char* dir, size_t num_points)
+{
+    try {
+        return new scalar_multiplication::Pippenger(std::string(dir), num_points);
+    } catch (std::exception const&) {
+        return nullptr;
+    }
+}
+void ref_delete_pippenger(void* p) { delete reinterpret_cast<scalar_multiplication::Pippenger*>(p); }
+size_t ref_pippenger_num_points(void* p) { return reinterpret_cast<scalar_multiplication::Pippenger*>(p)->get_num_points(); }
+void ref_pippenger_copy_table(void* p, void* out2n)
+{
+    auto* pp = reinterpret_cast<scalar_multiplication::Pippenger*>(p);
+    std::memcpy(out2n, pp->get_point_table(), pp->get_num_points() * 2 * sizeof(g1::affine_element));
+}
+int ref_pippenger_class_unsafe(void* p, const void* scalars, size_t from, size_t range, void* out_jac)
+{
+    try {
+        g1::element r = reinterpret_cast<scalar_multiplication::Pippenger*>(p)->pippenger_unsafe(
+            const_cast<fr*>(reinterpret_cast<const fr*>(scalars)), from, range);
+        *reinterpret_cast<g1::element*>(out_jac) = r;
+    } catch (std::exception const&) {
+        return 1;
+    }
+    return 0;
+}
+
 // ---- NTT
 // kind: 0 fft, 1 ifft, 2 coset_fft, 3 coset_ifft, 4 fft_with_constant, 5 ifft_with_constant,
 //       6 coset_fft_with_constant, 7 coset_fft_with_generator_shift   (polynomial_arithmetic.cpp:374-484)
