@@ -793,6 +793,60 @@ int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void*
     return tm.finish();
 }
 
+static void ntt_factor(unsigned log_n, unsigned& first_bits, unsigned& last_bits)
+{
+    // must mirror ntt_device's factorisation
+    const unsigned num_passes = log_n <= 16 ? 2 : (log_n <= 24 ? 3 : 4);
+    first_bits = log_n / num_passes + (0 < log_n % num_passes ? 1 : 0);
+    last_bits = log_n / num_passes + ((num_passes - 1) < log_n % num_passes ? 1 : 0);
+}
+
+int bbg_ntt_dist_layout(size_t n, int world, unsigned* in_pos, unsigned* out_pos)
+{
+    unsigned lg, rb = 0;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    while ((1 << rb) < world) ++rb;
+    unsigned first, last;
+    ntt_factor(lg, first, last);
+    if ((1 << rb) != world || lg < 12 || last < rb + 3 || first < rb + 3) {
+        set_last_error("ntt_dist: world must be a power of two with n >= 2^12 and at most 2^(digit - 3) ranks");
+        return BBG_ERR_ARG;
+    }
+    if (in_pos) *in_pos = last - rb;
+    if (out_pos) *out_pos = first - rb;
+    return BBG_OK;
+}
+
+int bbg_ntt_dist_dev(const void* d_src, void* d_dst, size_t n, int kind, size_t generator_size, const void* constant, int rank,
+                     int world, int phase, void* stream)
+{
+    GET_CTX();
+    unsigned lg;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    unsigned ip, op;
+    if ((rc = bbg_ntt_dist_layout(n, world, &ip, &op))) return rc;
+    if (rank < 0 || rank >= world || (phase != 0 && phase != 1) || (phase == 1 && d_src == d_dst)) {
+        set_last_error("ntt_dist: bad rank / phase / aliasing");
+        return BBG_ERR_ARG;
+    }
+    bool inverse;
+    NttScale pro, epi;
+    if ((rc = ntt_kind_params(kind, lg, generator_size, constant, inverse, pro, epi))) return rc;
+    NttDist dist;
+    dist.rank = (unsigned)rank;
+    dist.phase = phase;
+    while ((1 << dist.rank_bits) < world) ++dist.rank_bits;
+    if (dist.rank_bits == 0) {
+        // a single rank: phase 0 does the whole transform, phase 1 is a copy
+        if (phase == 0) return ntt_device(ctx, d_src, d_dst, lg, inverse, pro, epi, 0, 0, (cudaStream_t)stream);
+        BBG_CUDA(cudaMemcpyAsync(d_dst, d_src, n * 32, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return BBG_OK;
+    }
+    return ntt_device(ctx, d_src, d_dst, lg, inverse, pro, epi, 0, 0, (cudaStream_t)stream, dist);
+}
+
 static int coset_fft_ext_device(Context* ctx, void* d_coeffs, unsigned lg, size_t ext, cudaStream_t st)
 {
     unsigned lg_ext = 0;

@@ -30,8 +30,13 @@ struct NttScale {
     hf::Fr shift;       // geometric factor shift^i
     uint64_t size = 0;  // prologue only: applies to i < size
 };
+struct NttDist {
+    unsigned rank_bits = 0; // log2(number of ranks); 0 = single GPU
+    unsigned rank = 0;
+    int phase = 0;          // 0: every pass but the last (before the all-to-all); 1: the last pass (after it)
+};
 int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, bool inverse, const NttScale& pro, const NttScale& epi,
-               unsigned out_shift, unsigned out_off, cudaStream_t st);
+               unsigned out_shift, unsigned out_off, cudaStream_t st, const NttDist& dist = NttDist());
 hf::Fr ntt_root_of_unity(unsigned log_n);
 
 } // namespace bbg

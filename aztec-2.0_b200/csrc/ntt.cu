@@ -62,9 +62,25 @@ struct PassParams {
     fr epi_const;
     // output interleave for the extended coset FFT: natural index o lands at (o << out_shift) + out_off
     uint32_t out_shift, out_off;
+    // ---- multi-GPU four-step (one process per GPU; see ntt_device): this rank holds the sub-array whose index bits
+    // [rk_pos, rk_pos + rk_bits) equal rk_val, packed.  log_n / below / g1 describe the LOCAL array; twiddles and
+    // scalings use the true index, rebuilt by inserting the rank bits.
+    uint32_t tw_log_n;       // log2 of the full transform
+    uint32_t rk_bits, rk_pos, rk_val;
+    uint32_t mid_bits_total; // last pass: total width of digits 2..P-1
+    uint32_t split_low;      // last pass, after the all-to-all: a row is rk_bits source-rank chunks of 2^split_low elements,
+    uint32_t chunk_log;      //   chunk s starting at s << chunk_log
 };
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return __brev(x) >> (32 - bits); }
+__device__ __forceinline__ uint64_t insert_bits(uint64_t x, uint32_t pos, uint32_t bits, uint64_t val)
+{
+    return ((x >> pos) << (pos + bits)) | (val << pos) | (x & ((1ull << pos) - 1));
+}
+__device__ __forceinline__ uint64_t squeeze_bits(uint64_t x, uint32_t pos, uint32_t bits)
+{
+    return ((x >> (pos + bits)) << pos) | (x & ((1ull << pos) - 1));
+}
 
 __device__ __forceinline__ void smem_store(uint4* sm, uint32_t half_stride, uint32_t idx, const fr& v)
 {
@@ -160,8 +176,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
     const uint32_t tau = threadIdx.x & (R - 1);
     const uint32_t col = tau & 7;
     const uint32_t q = tau >> 3;                  // [0, R/8)
-    const uint64_t N = 1ull << P.log_n;
-    const uint64_t num_tiles = N >> (g + 3);
+    const uint64_t N = 1ull << P.tw_log_n;                  // full transform (twiddle exponents)
+    const uint64_t num_tiles = (1ull << P.log_n) >> (g + 3); // local array
     const uint64_t tile = (uint64_t)blockIdx.x * tiles_per_cta + tile_local;
     const bool active = tile < num_tiles;
     const uint32_t sm_base = tile_local * R * NTT_PAD; // this tile's rows inside the CTA's shared memory
@@ -191,9 +207,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
                 const uint32_t row = (uint32_t)j * rows8 + q;
                 const uint64_t a = in_base + ((uint64_t)row << P.below) + col;
                 x[j] = fe_load<FrParams>(P.src + a);
-                if (P.pro_lo != nullptr && a < P.pro_size) {
-                    fr s = fe_mul(fe_load_nc<FrParams>(P.pro_hi + (a >> P.pro_split)),
-                                  fe_load_nc<FrParams>(P.pro_lo + (a & ((1ull << P.pro_split) - 1))));
+                const uint64_t at = insert_bits(a, P.rk_pos, P.rk_bits, P.rk_val); // true coefficient index
+                if (P.pro_lo != nullptr && at < P.pro_size) {
+                    fr s = fe_mul(fe_load_nc<FrParams>(P.pro_hi + (at >> P.pro_split)),
+                                  fe_load_nc<FrParams>(P.pro_lo + (at & ((1ull << P.pro_split) - 1))));
                     x[j] = fe_mul(x[j], s);
                 }
             }
@@ -201,12 +218,20 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
     } else {
         // rows are contiguous in memory: stage through shared memory with lanes along the rows
         if (active) {
-            const uint32_t mid_bits_total = P.above - P.g1;
+            const uint32_t mid_bits_total = P.mid_bits_total;
 #pragma unroll 1
             for (uint32_t it = 0; it < 8; ++it) {
                 const uint32_t idx = it * R + tau;   // [0, 8R): column-major
                 const uint32_t c = idx >> g, row = idx & (R - 1);
-                const uint64_t a = ((((rest0 + c) << mid_bits_total) | mid) << g) + row;
+                const uint64_t hi_idx = ((rest0 + c) << mid_bits_total) | mid;
+                uint64_t a;
+                if (P.rk_bits == 0) {
+                    a = (hi_idx << g) + row;
+                } else {
+                    // after the all-to-all the row is split by source rank: chunk s holds i_P = (s, low)
+                    const uint32_t src_rank = row >> P.split_low, low = row & ((1u << P.split_low) - 1);
+                    a = ((uint64_t)src_rank << P.chunk_log) + (hi_idx << P.split_low) + low;
+                }
                 fr v = fe_load<FrParams>(P.src + a);
                 smem_store(sm, half_stride, sm_base + row * NTT_PAD + c, v);
             }
@@ -268,7 +293,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
         for (int j = 0; j < 8; ++j) {
             const uint32_t rho = (q << 3) | (uint32_t)j;
             const uint32_t o = bitrev(rho, g);
-            const uint64_t rest = rest0 + col;
+            const uint64_t rest = insert_bits(rest0 + col, P.rk_pos, P.rk_bits, P.rk_val);
             // inter-pass twiddle w_N^( 2^above * o * rest )
             uint64_t e = (((uint64_t)o * rest) << P.above) & (N - 1);
             if (e != 0) {
@@ -282,7 +307,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
         }
     } else {
         // natural-order output index: o_1 + sum_q o_q * 2^(bits before q) + o_P * 2^above
-        uint64_t obase = rest0 + col;
+        uint64_t obase = ((uint64_t)P.rk_val << P.g1) | (rest0 + col); // true o_1 (this rank owns its top rk_bits)
+        if (P.rk_bits == 0) obase = rest0 + col;
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
             if ((uint32_t)d < P.num_mid) {
@@ -301,7 +327,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
                               fe_load_nc<FrParams>(P.epi_lo + (o & ((1ull << P.epi_split) - 1))));
                 x[j] = fe_mul(x[j], s);
             }
-            fe_store(P.dst + ((o << P.out_shift) + P.out_off), x[j]);
+            const uint64_t ol = P.rk_bits ? squeeze_bits(o, P.g1, P.rk_bits) : o; // local slot of natural index o
+            fe_store(P.dst + ((ol << P.out_shift) + P.out_off), x[j]);
         }
     }
 }
@@ -448,8 +475,14 @@ static int ensure_big_table(Context* ctx, unsigned log_n, const fr** out, cudaSt
 //   pro : x[i] *= start * shift^i for i < size, before the transform
 //   epi : X[o] *= start (* shift^o), after the transform
 //   out index = (o << out_shift) + out_off inside dst
+//
+// Multi-GPU (dist.rank_bits = log2(world) > 0): the transform is the same P-pass factorisation with ONE exchange.
+//   phase 0: passes 1..P-1 on the local sub-array {i : bits [g_P - rb, g_P) of i == rank} (packed), all of whose
+//            sub-transforms are local because those bits lie below every digit handled so far;
+//   [all-to-all of equal contiguous chunks: chunk r' of every rank goes to rank r' -- done by the caller, NCCL]
+//   phase 1: the last pass on the received buffer; this rank ends up with {k : bits [g_1 - rb, g_1) of k == rank}, packed.
 int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, bool inverse, const NttScale& pro, const NttScale& epi,
-               unsigned out_shift, unsigned out_off, cudaStream_t st)
+               unsigned out_shift, unsigned out_off, cudaStream_t st, const NttDist& dist)
 {
     if (log_n > 28) {
         set_last_error("ntt: fr has 2-adicity 28, log2(n) must be <= 28");
@@ -459,6 +492,11 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
     hf::Fr root = ntt_root_of_unity(log_n);
     if (inverse) {
         root = hf::invert(root);
+    }
+    const unsigned rb = dist.rank_bits;
+    if (rb > 0 && (log_n < 12 || out_shift != 0 || out_off != 0 || dist.rank >= (1u << rb))) {
+        set_last_error("ntt: the multi-GPU path needs log2(n) >= 12 and no output interleave");
+        return BBG_ERR_ARG;
     }
     if (log_n <= 5) {
         SmallParams sp;
@@ -489,7 +527,7 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
     if ((rc = ensure_stage_tables(ctx, st))) return rc;
     const fr* tw_big = nullptr;
     if ((rc = ensure_big_table(ctx, log_n, &tw_big, st))) return rc;
-    if ((rc = ctx->ntt_scratch.reserve(N * sizeof(fr)))) return rc;
+    if (rb == 0 && (rc = ctx->ntt_scratch.reserve(N * sizeof(fr)))) return rc;
     fr* scratch = (fr*)ctx->ntt_scratch.p;
 
     // factorisation: P passes of nearly equal size, each 3..8 bits
@@ -529,21 +567,46 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         attr_set = true;
     }
 
+    if (rb > 0 && (gb[num_passes - 1] < rb + 3 || gb[0] < rb + 3)) {
+        set_last_error("ntt: too many ranks for this transform size");
+        return BBG_ERR_ARG;
+    }
+    const unsigned log_local = log_n - rb;
     unsigned above = 0;
     for (unsigned p = 0; p < num_passes; ++p) {
         PassParams pp;
         const bool last = (p == num_passes - 1);
-        pp.src = (p == 0) ? (const fr*)d_src : scratch;
-        pp.dst = last ? (fr*)d_dst : scratch;
+        if (rb == 0) {
+            pp.src = (p == 0) ? (const fr*)d_src : scratch;
+            pp.dst = last ? (fr*)d_dst : scratch;
+        } else {
+            if ((dist.phase == 0) == last) { // phase 0 runs every pass but the last, phase 1 only the last
+                above += gb[p];
+                continue;
+            }
+            pp.src = (p == 0 || last) ? (const fr*)d_src : (const fr*)d_dst; // middle passes run in place in dst
+            pp.dst = (fr*)d_dst;
+        }
         pp.tw_big = tw_big;
         pp.stage_tw = (const fr*)ctx->ntt_stage_tw[inverse ? 1 : 0] + ((1u << (gb[p] - 1)) - 1);
-        pp.log_n = log_n;
+        pp.log_n = log_local;
+        pp.tw_log_n = log_n;
         pp.g = gb[p];
         pp.above = above;
-        pp.below = log_n - above - gb[p];
+        pp.below = log_local - above - gb[p];
         pp.last = last;
         pp.inverse = inverse;
         pp.g1 = gb[0];
+        pp.rk_bits = rb;
+        pp.rk_pos = gb[num_passes - 1] - rb; // position of the rank bits inside the input index
+        pp.rk_val = dist.rank;
+        pp.mid_bits_total = log_n - gb[0] - gb[num_passes - 1];
+        pp.split_low = gb[num_passes - 1] - rb;
+        pp.chunk_log = log_local - rb;
+        if (rb > 0 && last) {
+            pp.g1 = gb[0] - rb;   // local o_1 (its top rb bits are this rank)
+            pp.below = 0;
+        }
         pp.num_mid = 0;
         for (int d = 0; d < 2; ++d) {
             pp.mid_bits[d] = pp.mid_src_shift[d] = pp.mid_dst_shift[d] = 0;
@@ -582,7 +645,7 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
             pp.out_shift = out_shift;
             pp.out_off = out_off;
         }
-        const uint64_t num_tiles = N >> (gb[p] + 3);
+        const uint64_t num_tiles = (N >> rb) >> (gb[p] + 3);
         const unsigned tiles_per_cta = NTT_THREADS >> gb[p];
         const unsigned blocks = (unsigned)((num_tiles + tiles_per_cta - 1) / tiles_per_cta);
         pr.mark(st, PH_NTT_PASS0 + (int)p);

@@ -26,7 +26,7 @@ OK, ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_SRS, ERR_IO = range(6)
  COSET_FFT_WITH_GENERATOR_SHIFT) = range(8)
 
 EXPORTS = [
-    "bbg_pippenger_bind_host_table", "bbg_set_auto_adopt", "bbg_bench_field_mul", "bbg_g1_add_affine_dev", "bbg_profile", "bbg_profile_read", "bbg_init", "bbg_shutdown", "bbg_last_error", "bbg_device_count", "bbg_kernel_launches", "bbg_last_device_ms",
+    "bbg_ntt_dist_layout", "bbg_ntt_dist_dev", "bbg_pippenger_bind_host_table", "bbg_set_auto_adopt", "bbg_bench_field_mul", "bbg_g1_add_affine_dev", "bbg_profile", "bbg_profile_read", "bbg_init", "bbg_shutdown", "bbg_last_error", "bbg_device_count", "bbg_kernel_launches", "bbg_last_device_ms",
     "bbg_malloc", "bbg_free", "bbg_new_pippenger", "bbg_new_pippenger_from_path", "bbg_new_pippenger_from_table",
     "bbg_new_pippenger_from_points", "bbg_new_pippenger_from_device_points", "bbg_delete_pippenger", "bbg_pippenger_num_points", "bbg_pippenger_get_point_table",
     "bbg_pippenger_device_points", "bbg_pippenger_unsafe", "bbg_pippenger_unsafe_dev", "bbg_pippenger", "bbg_msm_points",
@@ -92,6 +92,8 @@ lib.bbg_g1_op.argtypes = [_int, _vp, _vp, _vp, _sz]
 lib.bbg_init.argtypes = [_int]
 lib.bbg_profile.argtypes = [_int]
 lib.bbg_profile_read.argtypes = [_vp, _int]
+lib.bbg_ntt_dist_layout.argtypes = [_sz, _int, _vp, _vp]
+lib.bbg_ntt_dist_dev.argtypes = [_vp, _vp, _sz, _int, _sz, _vp, _int, _int, _int, _vp]
 lib.bbg_pippenger_bind_host_table.argtypes = [_vp, _vp]
 lib.bbg_set_auto_adopt.argtypes = [_int]
 lib.bbg_bench_field_mul.argtypes = [_int, _int, _vp]
@@ -376,6 +378,22 @@ def coset_fft_ext(coeffs, n, domain_extension, stream=None):
     else:
         _check(lib.bbg_coset_fft_ext_dev(coeffs.data_ptr(), n, domain_extension, _stream_ptr(stream)))
     return coeffs
+
+
+def ntt_dist_layout(n, world):
+    """(in_pos, out_pos): rank r holds input indices whose bits [in_pos, in_pos + log2 world) equal r (packed), and
+    ends with the output indices whose bits [out_pos, ...) equal r."""
+    a, b = ctypes.c_uint(0), ctypes.c_uint(0)
+    _check(lib.bbg_ntt_dist_layout(n, world, ctypes.cast(ctypes.pointer(a), _vp), ctypes.cast(ctypes.pointer(b), _vp)))
+    return a.value, b.value
+
+
+def ntt_dist_phase(src, dst, n, kind, rank, world, phase, generator_size=0, constant=None, stream=None):
+    """One phase of the multi-GPU NTT on torch CUDA tensors (include/bbg.h bbg_ntt_dist_dev)."""
+    k = None if constant is None else _np(constant, 4)
+    _check(lib.bbg_ntt_dist_dev(src.data_ptr(), dst.data_ptr(), n, kind, generator_size, None if k is None else k.ctypes.data,
+                                rank, world, phase, _stream_ptr(stream)))
+    return dst
 
 
 def domain_constants(n):

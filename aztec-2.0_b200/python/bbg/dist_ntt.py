@@ -1,0 +1,64 @@
+"""Multi-GPU four-step NTT plumbing (one process per GPU, torch.distributed over NCCL).
+
+The device work is libbbg's (bbg_ntt_dist_dev, csrc/ntt.cu): phase 0 = every pass but the last on this rank's packed
+sub-array, phase 1 = the last pass after ONE all-to-all of equal contiguous chunks.  This module only moves chunks
+(torch.distributed.all_to_all_single) and converts between a natural-order array and the per-rank layouts:
+
+    input  shard of rank r : x[i] with bits [in_pos,  in_pos  + log2 world) of i == r, packed in index order
+    output shard of rank r : X[k] with bits [out_pos, out_pos + log2 world) of k == r, packed in index order
+
+`simulate` runs all ranks one after the other on ONE device with the exchange done by slicing -- the same kernels and
+index maths as the multi-process path -- so the N > 1 data path is parity-tested on a single GPU.
+"""
+import numpy as np
+
+
+def extract_shard(x, pos, world, rank):
+    """x: (n, 4) natural order (numpy or torch). Returns the packed (n / world, 4) sub-array of `rank`."""
+    n = x.shape[0]
+    low = 1 << pos
+    return x.reshape(n // (low * world), world, low, 4)[:, rank].reshape(n // world, 4)
+
+
+def insert_shard(out, shard, pos, world, rank):
+    n = out.shape[0]
+    low = 1 << pos
+    out.reshape(n // (low * world), world, low, 4)[:, rank] = shard.reshape(n // (low * world), low, 4)
+
+
+def ntt_sharded(bbg, local_in, n, kind, rank, world, generator_size=0, constant=None, group=None):
+    """local_in: torch CUDA int64 tensor (n / world, 4) = this rank's input shard.  Returns this rank's output shard."""
+    import torch
+    import torch.distributed as dist
+    mid = torch.empty_like(local_in)
+    bbg.ntt_dist_phase(local_in, mid, n, kind, rank, world, 0, generator_size, constant)
+    if world == 1:
+        return mid
+    recv = torch.empty_like(mid)
+    dist.all_to_all_single(recv, mid, group=group)  # chunk r of every rank -> rank r, in source-rank order
+    out = torch.empty_like(mid)
+    bbg.ntt_dist_phase(recv, out, n, kind, rank, world, 1, generator_size, constant)
+    return out
+
+
+def simulate(bbg, x, kind, world, generator_size=0, constant=None):
+    """All `world` ranks on one device. x: torch CUDA int64 (n, 4) natural order -> natural-order result."""
+    import torch
+    n = x.shape[0]
+    in_pos, out_pos = bbg.ntt_dist_layout(n, world)
+    m = n // world
+    mids = []
+    for r in range(world):
+        src = extract_shard(x, in_pos, world, r).contiguous()
+        mid = torch.empty_like(src)
+        bbg.ntt_dist_phase(src, mid, n, kind, r, world, 0, generator_size, constant)
+        mids.append(mid)
+    out = torch.empty_like(x)
+    c = m // world
+    for r in range(world):
+        recv = torch.cat([mids[s][r * c:(r + 1) * c] for s in range(world)], dim=0).contiguous()
+        dst = torch.empty_like(recv)
+        bbg.ntt_dist_phase(recv, dst, n, kind, r, world, 1, generator_size, constant)
+        insert_shard(out, dst, out_pos, world, r)
+    torch.cuda.synchronize()
+    return out

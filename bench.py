@@ -225,6 +225,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     torch.cuda.set_device(local)
     bbg.init(local)
     dev = torch.device("cuda", local)
@@ -366,7 +368,7 @@ def run_ours(args):
 
     # ---- NTT family at 2^ntt_log_n
     if not args.no_ntt:
-        line["ntt"] = bench_ntt(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq_muls, barrier, max_over_ranks, world)
+        line["ntt"] = bench_ntt(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq_muls, barrier, max_over_ranks, world, rank)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -391,7 +393,50 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_ntt(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq_muls, barrier, max_over_ranks, world):
+def bench_ntt_sharded(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq_muls, barrier, max_over_ranks, world, rank):
+    """N > 1: ONE transform of world * 2^ntt_log_n elements, four-step with an NCCL all-to-all; every rank
+    holds 2^ntt_log_n elements (weak scaling)."""
+    import torch.distributed as dist
+    from bbg import dist_ntt
+    lg_local = args.ntt_log_n
+    rb = world.bit_length() - 1
+    if (1 << rb) != world:
+        return {"unavailable": "the four-step NTT needs a power-of-two number of ranks"}
+    n = (1 << lg_local) * world
+    local = torch.from_numpy(inputs.fr_elements(2000 + rank, 1 << lg_local).view(np.int64)).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    per = {}
+    launches0 = bbg.kernel_launches()
+    for name, kind in (("fft", bbg.FFT), ("ifft", bbg.IFFT), ("coset_fft", bbg.COSET_FFT)):
+        for _ in range(W):
+            dist_ntt.ntt_sharded(bbg, local, n, kind, rank, world)
+        barrier()
+        ms = 0.0
+        for _ in range(K):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()
+            dist.barrier()
+            a.record()
+            dist_ntt.ntt_sharded(bbg, local, n, kind, rank, world)
+            b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+        barrier()
+        per[name] = {"ms": max_over_ranks(ms) / K}
+        per[name]["elements_per_s"] = n / (per[name]["ms"] * 1e-3)
+    launches = bbg.kernel_launches() - launches0
+    mean_ms = statistics.mean(v["ms"] for v in per.values())
+    return {
+        "metric": "bn254_fr_ntt_elements_per_s", "value": n / (mean_ms * 1e-3), "unit": "elements/s", "log_n": lg_local + rb,
+        "per_kind": per, "ms_per_transform": mean_ms, "gpu_launches": launches,
+        "scaling": "weak: one 2^%d-point transform, 2^%d elements per GPU, four-step passes + one NCCL all-to-all of %d B per GPU"
+                   % (lg_local + rb, lg_local, (32 << lg_local) * (world - 1) // world),
+    }
+
+
+def bench_ntt(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq_muls, barrier, max_over_ranks, world, rank=0):
+    if world > 1:
+        return bench_ntt_sharded(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq_muls, barrier, max_over_ranks, world, rank)
     lg = args.ntt_log_n
     n = 1 << lg
     x_host = bbg.pinned_empty((n, 4))

@@ -122,6 +122,20 @@ int bbg_read_g1_elements_from_buffer(void* elements, const char* buffer, size_t 
  * constant: one fr (Montgomery) for kinds 4..7, ignored otherwise. */
 int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant);
 int bbg_ntt_dev(void* d_coeffs, size_t n, int kind, size_t generator_size, const void* constant, void* stream);
+/* Multi-GPU four-step NTT, one process per GPU, world = 2^k ranks, n >= 2^12.  The transform is the same
+ * pass factorisation n = n_1 ... n_P as on one GPU, with ONE exchange between pass P-1 and pass P:
+ *   phase 0 : d_src = this rank's input sub-array {x[i] : bits [in_pos, in_pos + k) of i == rank}, packed in index order
+ *             (n / world elements); runs passes 1..P-1; d_dst (n / world elements, may equal d_src) receives the
+ *             intermediate, whose world equal contiguous chunks are the all-to-all send buffers (chunk r -> rank r);
+ *   exchange: the caller's all-to-all (NCCL ncclSend/ncclRecv group, torch.distributed.all_to_all_single), chunk from
+ *             rank s landing at offset s * n / world^2 of the receive buffer;
+ *   phase 1 : d_src = receive buffer, d_dst (distinct) = this rank's output sub-array {X[k] : bits [out_pos, out_pos + k)
+ *             of k == rank}, packed in index order.
+ * bbg_ntt_dist_layout gives in_pos / out_pos for (n, world).  Same kinds, scalings and bit-exact results as bbg_ntt. */
+int bbg_ntt_dist_layout(size_t n, int world, unsigned* in_pos, unsigned* out_pos);
+int bbg_ntt_dist_dev(const void* d_src, void* d_dst, size_t n, int kind, size_t generator_size, const void* constant, int rank,
+                     int world, int phase, void* stream);
+
 /* coset_fft(coeffs, small_domain, large_domain, domain_extension) (polynomial_arithmetic.cpp:401-456):
  * coeffs holds ext*n elements, the first n are the input; output interleaved out[ext*i + k]. */
 int bbg_coset_fft_ext(void* coeffs, size_t n, size_t domain_extension);

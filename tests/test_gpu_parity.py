@@ -291,3 +291,38 @@ def test_msm_fixed_base_levels(bbg, orc, srs_mini, levels, c, monkeypatch):
     assert orc.jac_to_buffer(pip.pippenger_unsafe(sc[:500], 77, 500)) == orc.jac_to_buffer(orc.pippenger(sc[:500], pts[77:577], stride=1))
     one = np.repeat(inputs.fr_elements(5, 1), n, axis=0)  # one bucket holds everything: exercises every merge level
     assert orc.jac_to_buffer(pip.pippenger_unsafe(one, 0, n)) == orc.jac_to_buffer(orc.pippenger(one, pts[:n], stride=1))
+
+
+@pytest.mark.parametrize("lg,world", [(12, 2), (14, 4), (16, 8), (18, 8), (20, 2)])
+def test_ntt_multi_gpu_data_path_simulated(bbg, orc, lg, world):
+    """The multi-GPU four-step NTT (phase 0 / all-to-all / phase 1, csrc/ntt.cu + bbg/dist_ntt.py) with every rank run in
+    turn on one device: same kernels, same index maths as the torchrun path; must equal the single-array transform."""
+    import torch
+    from bbg import dist_ntt
+    n = 1 << lg
+    x = inputs.fr_elements(3000 + lg, n, coarse_fraction=0.25)
+    const = inputs.fr_elements(3100 + lg, 1)[0]
+    xt = torch.from_numpy(x.view(np.int64)).cuda()
+    for kind, gs in ((bbg.FFT, 0), (bbg.COSET_FFT, n // 4), (bbg.COSET_IFFT, 0), (bbg.IFFT_WITH_CONSTANT, 0)):
+        got = dist_ntt.simulate(bbg, xt, kind, world, generator_size=gs, constant=const).cpu().numpy().view(np.uint64)
+        exp = bbg.ntt(x.copy(), kind, generator_size=gs, constant=const)
+        assert np.array_equal(canon(orc, got), canon(orc, exp)), (lg, world, kind)
+    if lg <= 14:
+        assert np.array_equal(canon(orc, exp), canon(orc, orc.ntt(po.NTT_IFFT_CONST, x, constant=const)))
+
+
+def test_multi_process_nccl_paths(bbg):
+    """Real N > 1 run (torchrun, NCCL): needs >= 2 visible GPUs, skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "dist_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") == world
