@@ -211,7 +211,7 @@ def run_reference(args):
             per[name] = nn / (sum(t) / len(t))
         line["ntt"] = {"metric": "bn254_fr_ntt_elements_per_s", "value": statistics.mean(per.values()), "unit": "elements/s",
                        "per_kind": per, "log_n": args.ntt_log_n, "sample": nsample, "cores": cores, "kind": kind}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -388,7 +388,7 @@ def run_ours(args):
         line["cpu_baseline"] = None
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -493,8 +493,26 @@ def bench_ntt(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq_muls, b
     }
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL's version banner, library chatter) was
+    re-routed to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
