@@ -395,7 +395,7 @@ void bbg_shutdown(void)
     }
     DevBuf* bufs[] = { &g_ctx->msm_scalars, &g_ctx->msm_counts, &g_ctx->msm_offsets, &g_ctx->msm_cursors, &g_ctx->msm_sorted,
                        &g_ctx->msm_buckets, &g_ctx->msm_partials, &g_ctx->msm_reduce, &g_ctx->msm_scan_tmp, &g_ctx->msm_result,
-                       &g_ctx->msm_points, &g_ctx->ntt_data, &g_ctx->ntt_scratch, &g_ctx->ntt_pro, &g_ctx->ntt_epi, &g_ctx->ntt_small };
+                       &g_ctx->msm_points, &g_ctx->msm_lvl_offsets, &g_ctx->msm_pairs_a, &g_ctx->msm_pairs_b, &g_ctx->msm_pair_pre, &g_ctx->msm_pair_meta, &g_ctx->msm_pts0, &g_ctx->ntt_data, &g_ctx->ntt_scratch, &g_ctx->ntt_pro, &g_ctx->ntt_epi, &g_ctx->ntt_small };
     for (auto* b : bufs) b->release();
     cudaEventDestroy(g_ctx->ev_a);
     cudaEventDestroy(g_ctx->ev_b);

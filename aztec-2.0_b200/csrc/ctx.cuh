@@ -57,7 +57,7 @@ struct DevBuf {
 // Optional per-phase device timing (bbg_profile): CUDA events recorded on the launching stream at
 // phase boundaries; bench.py reads the per-phase milliseconds for the roofline of the dominant kernel.
 enum Phase {
-    PH_MSM_DIGITS = 0, PH_MSM_SCAN, PH_MSM_SCATTER, PH_MSM_ACCUMULATE, PH_MSM_FIXUP, PH_MSM_REDUCE, PH_MSM_COMBINE,
+    PH_MSM_DIGITS = 0, PH_MSM_SCAN, PH_MSM_SCATTER, PH_MSM_PAIRS, PH_MSM_ACCUMULATE, PH_MSM_FIXUP, PH_MSM_REDUCE, PH_MSM_COMBINE,
     PH_NTT_TABLES, PH_NTT_PASS0, PH_NTT_PASS1, PH_NTT_PASS2, PH_NTT_PASS3, PH_COUNT
 };
 struct Profiler {
@@ -84,7 +84,8 @@ struct Context {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // MSM workspaces
     DevBuf msm_scalars, msm_counts, msm_offsets, msm_cursors, msm_sorted, msm_buckets, msm_partials, msm_reduce,
-        msm_scan_tmp, msm_result, msm_points;
+        msm_scan_tmp, msm_result, msm_points, msm_lvl_offsets, msm_pairs_a, msm_pairs_b, msm_pair_pre, msm_pair_meta, msm_pts0;
+    void* inv_fix_fq = nullptr; // inv.cuh fix-up constants (fq)
     // NTT workspaces
     DevBuf ntt_data, ntt_scratch, ntt_pro, ntt_epi, ntt_small;
     std::map<unsigned, void*> ntt_twiddles; // log2n -> w_N^e table (N entries)

@@ -23,6 +23,7 @@
 // The arithmetic below is plain C++ on 8 x u32 limbs so that the same source is unit-tested on the host
 // (tests/test_host_inverse.py builds it with g++); nvcc turns the carry chains into IADD3.X.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 #if defined(__CUDACC__)

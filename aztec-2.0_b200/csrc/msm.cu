@@ -35,6 +35,7 @@
 
 #include "g1.cuh"
 #include "internal.hpp"
+#include "inv.cuh"
 
 namespace bbg {
 
@@ -51,11 +52,18 @@ struct DigitParams {
     uint32_t base;         // table entry of scalar 0 (Pippenger `from`)
 };
 
-template <bool SCATTER>
+// MODE 0: histogram of bucket sizes.  MODE 1: counting-sort scatter of schedule words (table index << 1 | negate).
+// MODE 2: counting-sort scatter of the POINTS themselves (sign applied): thread i reads entry i of every level --
+// coalesced -- and the pairwise passes / the accumulation then stream the bucket-ordered copy instead of gathering.
+enum { DIG_HISTOGRAM = 0, DIG_SCATTER_INDEX = 1, DIG_SCATTER_POINTS = 2 };
+template <int MODE>
 __global__ void __launch_bounds__(256) k_msm_digits(const fr_t* __restrict__ scalars,
                                                     const DigitParams P,
                                                     uint32_t* __restrict__ counters,
-                                                    uint32_t* __restrict__ sorted)
+                                                    uint32_t* __restrict__ sorted,
+                                                    const affine_t* __restrict__ points,
+                                                    uint32_t point_stride,
+                                                    affine_t* __restrict__ pts_out)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) {
@@ -89,9 +97,17 @@ __global__ void __launch_bounds__(256) k_msm_digits(const fr_t* __restrict__ sca
         carry = neg;
         if (mag) {
             uint32_t g = set * P.B + (mag - 1);
-            if (SCATTER) {
+            if (MODE == DIG_SCATTER_INDEX) {
                 uint32_t dst = atomicAdd(&counters[g], 1u);
                 sorted[dst] = ((level * P.level_stride + P.base + i) << 1) | neg;
+            } else if (MODE == DIG_SCATTER_POINTS) {
+                // (re)load per window: with fixed-base levels every window has its own point; with L == 1 the
+                // reload hits L1
+                affine_t pt = affine_load(points + (size_t)(level * P.level_stride + P.base + i) * point_stride);
+                if (neg) pt.y = fe_neg(pt.y);
+                uint32_t dst = atomicAdd(&counters[g], 1u);
+                fe_store(&pts_out[dst].x, pt.x);
+                fe_store(&pts_out[dst].y, pt.y);
             } else {
                 atomicAdd(&counters[g], 1u);
             }
@@ -139,14 +155,21 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ tile_sums)
+// The scans are batched over blockIdx.y: row y scans ceil(in[i] / 2^(shift_base + y)) -- row 0 with shift 0 is the
+// plain bucket histogram, the other rows are the bucket sizes after y rounds of pairwise additions (k_msm_pair_pass).
+__device__ __forceinline__ uint32_t ceil_shift(uint32_t v, uint32_t sh) { return (v + ((1u << sh) - 1u)) >> sh; }
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ tile_sums,
+                                                                 uint32_t shift_base)
 {
     __shared__ uint32_t smem[33];
+    const uint32_t sh = shift_base + blockIdx.y;
+    tile_sums += (size_t)blockIdx.y * SCAN_TILE;
     size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     uint32_t s = 0;
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; ++j) {
-        if (base + j < n) s += in[base + j];
+        if (base + j < n) s += ceil_shift(in[base + j], sh);
     }
     uint32_t total;
     block_exclusive_scan(s, smem, total);
@@ -155,6 +178,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t*
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(uint32_t* __restrict__ tile_sums, unsigned num_tiles)
 {
     __shared__ uint32_t smem[33];
+    tile_sums += (size_t)blockIdx.y * SCAN_TILE;
     uint32_t v[SCAN_ITEMS];
     uint32_t s = 0;
 #pragma unroll
@@ -176,15 +200,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
                                                              size_t n,
                                                              const uint32_t* __restrict__ tile_prefix,
                                                              uint32_t* __restrict__ out,
-                                                             uint32_t* __restrict__ out_copy)
+                                                             uint32_t* __restrict__ out_copy, // may be null
+                                                             uint32_t shift_base)
 {
     __shared__ uint32_t smem[33];
+    const uint32_t sh = shift_base + blockIdx.y;
+    tile_prefix += (size_t)blockIdx.y * SCAN_TILE;
+    out += (size_t)blockIdx.y * (n + 1);
     size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t s = 0;
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; ++j) {
-        v[j] = (base + j < n) ? in[base + j] : 0;
+        v[j] = (base + j < n) ? ceil_shift(in[base + j], sh) : 0;
         s += v[j];
     }
     uint32_t total;
@@ -193,7 +221,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
     for (int j = 0; j < SCAN_ITEMS; ++j) {
         if (base + j < n) {
             out[base + j] = ex;
-            out_copy[base + j] = ex;
+            if (out_copy) out_copy[base + j] = ex;
         }
         ex += v[j];
         if (base + j + 1 == n) {
@@ -239,6 +267,9 @@ __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* __restrict__
     return lo;
 }
 
+// DIRECT: the entry at position pos IS points[pos] (the output of the pairwise passes); otherwise it is the schedule
+// word sorted[pos] = (table index << 1) | negate.
+template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS, 4) k_msm_accumulate(const uint32_t* __restrict__ sorted,
                                                                    const uint32_t* __restrict__ offsets, // G+1
                                                                    uint32_t G,
@@ -274,16 +305,16 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_msm_accumulate(const uint32_
     bool a_set = false, b_set = false;
     xyzz_t acc = xyzz_infinity();
     uint32_t pos = start;
-    uint32_t v = __ldg(sorted + pos);
-    affine_t pt = affine_load(points + (size_t)(v >> 1) * point_stride);
+    uint32_t v = DIRECT ? 0u : __ldg(sorted + pos);
+    affine_t pt = affine_load(DIRECT ? points + pos : points + (size_t)(v >> 1) * point_stride);
     while (true) {
         // prefetch the next entry's point while this one is being added
         uint32_t vn = 0;
         affine_t ptn;
         const bool more = pos + 1 < end;
         if (more) {
-            vn = __ldg(sorted + pos + 1);
-            ptn = affine_load(points + (size_t)(vn >> 1) * point_stride);
+            vn = DIRECT ? 0u : __ldg(sorted + pos + 1);
+            ptn = affine_load(DIRECT ? points + pos + 1 : points + (size_t)(vn >> 1) * point_stride);
         }
         if (!affine_is_inf(pt)) {
             if (v & 1) {
@@ -325,6 +356,263 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_msm_accumulate(const uint32_
     if (!b_set) slot_b->bucket = SLOT_NONE;
     if (a_set || b_set) {
         atomicAdd(pending, 1u); // something for the merge levels to do
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4a. pairwise affine additions with one shared inversion per CTA batch ("batched affine"; optional path)
+// ------------------------------------------------------------------------------------------------
+// The reference sums a bucket's points in affine coordinates, pairing them level by level and sharing one field
+// inversion among all the additions of a level (scalar_multiplication.cpp:273-401 add_affine_points, :523-718
+// evaluate_addition_chains): 5M + 1S per addition instead of 8M + 2S for a projective mixed addition.  Same idea
+// here, laid out for the GPU: one launch per level; level j holds, bucket after bucket, the ceil(m / 2^j) partial
+// sums of every bucket (offsets from the batched scan), output slot q of a bucket is input slots 2q and 2q+1 (or a
+// copy of 2q when the count is odd).  A thread owns K consecutive output slots, a CTA batch is PAIR_THREADS * K
+// slots:
+//   forward : d_i = x2 - x1 per slot, running product stored per slot (Montgomery's trick)
+//   combine : warp 0 multiplies the 8 thread products of each lane column, inverts the 32 column products -- one
+//             inversion per lane, all lanes at once, on the ALU pipe (inv.cuh) -- and hands every thread the inverse
+//             of its own product
+//   backward: 1/d_i from the running inverse and the stored prefix, then lambda, x3, y3.
+// Exceptional cases keep the batch intact by substituting the denominator: equal points double (d = 2y, numerator
+// 3x^2), opposite points give infinity (d = 1), an infinite operand or a missing partner copies (d = 1).
+static constexpr int PAIR_THREADS = 256;
+static constexpr int PAIR_K_MAX = 64;
+static constexpr int PAIR_WARPS = PAIR_THREADS / 32;
+enum : uint32_t { PK_NONE = 0, PK_ADD = 1, PK_DBL = 2, PK_COPY1 = 3, PK_COPY2 = 4, PK_INF = 5 };
+
+// The running products and the per-slot bookkeeping of a batch live in global scratch indexed by output slot (they
+// are written in the forward sweep and read back once in the backward sweep, mostly out of L2): a thread can then
+// own tens of slots, which is what amortises the inversion.
+struct PairSmem {
+    uint4 tp[2][PAIR_THREADS];   // thread products, then their inverses
+    uint4 wp[2][PAIR_WARPS][32]; // per lane column: products over warps 0..w
+};
+
+__device__ __forceinline__ void sm_put(uint4* lo, uint4* hi, const fq& v)
+{
+    *lo = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    *hi = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ fq sm_get(const uint4* lo, const uint4* hi)
+{
+    const uint4 a = *lo, b = *hi;
+    fq r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+// Every lane of a full warp inverts its own Montgomery-form value (non-zero mod p): result is the Montgomery form
+// of the inverse.  fix = the C_k table of inv.cuh.
+__device__ __forceinline__ fq fq_inv_warp(const fq& a, const uint32_t* __restrict__ fix)
+{
+    const fq ar = fe_reduce_once(a);
+    uint32_t pl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pl[i] = FqParams::P(i);
+    inv::Kaliski st;
+    st.init(ar.l, pl);
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, st.alive())) {
+        st.step();
+    }
+    fq y;
+    st.finish(y.l, pl);
+    uint32_t k = st.k < inv::K_MIN ? inv::K_MIN : (st.k > inv::K_MAX ? inv::K_MAX : st.k);
+    const fq c = fe_load_nc<FqParams>(fix + (size_t)(k - inv::K_MIN) * 8);
+    return fe_mul(y, c);
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <bool PASS0> struct PairSrc {
+    const uint32_t* sorted;
+    const affine_t* pts;
+    uint32_t stride;
+    __device__ __forceinline__ fq x(uint32_t pos) const
+    {
+        if (PASS0) {
+            const uint32_t v = __ldg(sorted + pos);
+            return fe_load_nc<FqParams>(&pts[(size_t)(v >> 1) * stride].x);
+        }
+        return fe_load_nc<FqParams>(&pts[pos].x);
+    }
+    __device__ __forceinline__ affine_t point(uint32_t pos) const
+    {
+        if (PASS0) {
+            const uint32_t v = __ldg(sorted + pos);
+            affine_t p = affine_load(pts + (size_t)(v >> 1) * stride);
+            if (v & 1) p.y = fe_neg(p.y);
+            return p;
+        }
+        return affine_load(pts + pos);
+    }
+};
+
+// PASS0: the inputs are schedule words (gather from the level tables); otherwise the previous level's points.
+template <bool PASS0>
+__global__ void __launch_bounds__(PAIR_THREADS, 2) k_msm_pair_pass(const uint32_t* __restrict__ sorted,
+                                                                   const affine_t* __restrict__ in,
+                                                                   uint32_t point_stride,
+                                                                   const uint32_t* __restrict__ off_in,  // G+1
+                                                                   const uint32_t* __restrict__ off_out, // G+1
+                                                                   uint32_t G,
+                                                                   affine_t* __restrict__ out,
+                                                                   const uint32_t* __restrict__ inv_fix,
+                                                                   uint32_t K,                 // slots per thread
+                                                                   uint4* __restrict__ pre,    // 2 x uint4 per output slot
+                                                                   uint2* __restrict__ meta)   // (input position, kind) per slot
+{
+    __shared__ PairSmem sm;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t total = __ldg(off_out + G);
+    const uint64_t cta_base = (uint64_t)blockIdx.x * ((uint64_t)PAIR_THREADS * K);
+    if (cta_base >= total) {
+        return; // whole CTA past the end (the grid is sized for the worst case)
+    }
+    const uint64_t o0_64 = cta_base + (uint64_t)tid * K;
+    const uint32_t o0 = (uint32_t)(o0_64 < total ? o0_64 : total);
+    const uint32_t n_slots = min(K, total - o0);
+    const PairSrc<PASS0> src{ sorted, in, point_stride };
+    const uint32_t in_total = __ldg(off_in + G);
+
+    // ---- forward
+    fq run = fe_one<FqParams>();
+    {
+        uint32_t b = 0, ob = 0, oe = 0, ib = 0, ie = 0;
+        if (n_slots) {
+            b = upper_bound_u32(off_out, G + 1, o0) - 1;
+            ob = __ldg(off_out + b);
+            oe = __ldg(off_out + b + 1);
+            ib = __ldg(off_in + b);
+            ie = __ldg(off_in + b + 1);
+        }
+#pragma unroll 1
+        for (uint32_t i = 0; i < n_slots; ++i) {
+            uint32_t kind = PK_NONE, p1 = 0;
+            {
+                const uint32_t o = o0 + i;
+                if (o >= oe) {
+                    do { // next non-empty bucket
+                        ++b;
+                        ob = oe;
+                        oe = __ldg(off_out + b + 1);
+                    } while (oe == ob);
+                    ib = __ldg(off_in + b);
+                    ie = __ldg(off_in + b + 1);
+                }
+                p1 = ib + 2 * (o - ob);
+                if (!PASS0 && p1 + 5 < in_total) { // the next slots' operands follow in memory: pull them into L1 early
+                    prefetch_l1(in + p1 + 4);
+                    prefetch_l1(in + p1 + 5);
+                }
+                const fq x1 = src.x(p1);
+                if (p1 + 1 >= ie) {
+                    kind = PK_COPY1;
+                } else {
+                    const fq x2 = src.x(p1 + 1);
+                    if (x1.l[7] & INF_BIT) {
+                        kind = PK_COPY2;
+                    } else if (x2.l[7] & INF_BIT) {
+                        kind = PK_COPY1;
+                    } else {
+                        fq d = fe_sub(x2, x1);
+                        kind = PK_ADD;
+                        if (__builtin_expect(fe_is_zero(d), 0)) {
+                            const affine_t a = src.point(p1), c = src.point(p1 + 1);
+                            if (fe_is_zero(fe_sub(a.y, c.y))) {
+                                kind = PK_DBL;
+                                d = fe_dbl(a.y); // y != 0 on a curve of odd order
+                            } else {
+                                kind = PK_INF;
+                            }
+                        }
+                        if (kind != PK_INF) {
+                            run = fe_mul(run, d);
+                        }
+                    }
+                }
+            }
+            sm_put(&pre[2 * (size_t)(o0 + i)], &pre[2 * (size_t)(o0 + i) + 1], run);
+            meta[o0 + i] = make_uint2(p1, kind);
+        }
+    }
+
+    // ---- combine: inverse of every thread's product
+    sm_put(&sm.tp[0][tid], &sm.tp[1][tid], run);
+    __syncthreads();
+    if (tid < 32) {
+        fq acc = sm_get(&sm.tp[0][tid], &sm.tp[1][tid]);
+        sm_put(&sm.wp[0][0][tid], &sm.wp[1][0][tid], acc);
+#pragma unroll 1
+        for (uint32_t w = 1; w < PAIR_WARPS; ++w) {
+            acc = fe_mul(acc, sm_get(&sm.tp[0][w * 32 + tid], &sm.tp[1][w * 32 + tid]));
+            sm_put(&sm.wp[0][w][tid], &sm.wp[1][w][tid], acc);
+        }
+        fq inv_acc = fq_inv_warp(acc, inv_fix);
+#pragma unroll 1
+        for (uint32_t w = PAIR_WARPS - 1; w >= 1; --w) {
+            const fq t = sm_get(&sm.tp[0][w * 32 + tid], &sm.tp[1][w * 32 + tid]);
+            const fq below = sm_get(&sm.wp[0][w - 1][tid], &sm.wp[1][w - 1][tid]);
+            sm_put(&sm.tp[0][w * 32 + tid], &sm.tp[1][w * 32 + tid], fe_mul(inv_acc, below));
+            inv_acc = fe_mul(inv_acc, t);
+        }
+        sm_put(&sm.tp[0][tid], &sm.tp[1][tid], inv_acc);
+    }
+    __syncthreads();
+
+    // ---- backward
+    fq inv_run = sm_get(&sm.tp[0][tid], &sm.tp[1][tid]);
+#pragma unroll 1
+    for (int i = (int)n_slots - 1; i >= 0; --i) {
+        const uint2 mt = meta[o0 + (uint32_t)i];
+        const uint32_t kind = mt.y;
+        const uint32_t p1 = mt.x;
+        if (!PASS0 && i >= 2) { // descending sweep: the slots before this one
+            if (p1 >= 4) {
+                prefetch_l1(in + p1 - 4);
+                prefetch_l1(in + p1 - 3);
+            }
+            prefetch_l1(&pre[2 * (size_t)(o0 + i - 2)]);
+        }
+        affine_t* dst = out + (o0 + (uint32_t)i);
+        if (kind >= PK_COPY1) {
+            affine_t r;
+            if (kind == PK_INF) {
+                r.x = fe_zero<FqParams>();
+                r.y = fe_zero<FqParams>();
+                r.x.l[7] |= INF_BIT;
+            } else {
+                r = src.point(kind == PK_COPY1 ? p1 : p1 + 1);
+            }
+            fe_store(&dst->x, r.x);
+            fe_store(&dst->y, r.y);
+            continue;
+        }
+        const affine_t a = src.point(p1);
+        fq x2, d, num;
+        if (kind == PK_ADD) {
+            const affine_t c = src.point(p1 + 1);
+            x2 = c.x;
+            d = fe_sub(c.x, a.x);
+            num = fe_sub(c.y, a.y);
+        } else {
+            x2 = a.x;
+            d = fe_dbl(a.y);
+            const fq xx = fe_sqr(a.x);
+            num = fe_add(fe_dbl(xx), xx);
+        }
+        fq inv_d = inv_run;
+        if (i > 0) {
+            inv_d = fe_mul(inv_run, sm_get(&pre[2 * (size_t)(o0 + i - 1)], &pre[2 * (size_t)(o0 + i - 1) + 1]));
+            inv_run = fe_mul(inv_run, d);
+        }
+        const fq lam = fe_mul(num, inv_d);
+        const fq x3 = fe_sub(fe_sub(fe_sqr(lam), a.x), x2);
+        const fq y3 = fe_sub(fe_mul(lam, fe_sub(a.x, x3)), a.y);
+        fe_store(&dst->x, x3);
+        fe_store(&dst->y, y3);
     }
 }
 
@@ -645,19 +933,21 @@ __global__ void __launch_bounds__(256) k_compact_even(const uint4* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
-static int exclusive_scan(Context* ctx, const uint32_t* d_in, size_t n, uint32_t* d_out, uint32_t* d_out_copy, cudaStream_t st)
+// rows >= 1: row y of d_out (n + 1 entries each) = exclusive scan of ceil(d_in / 2^(shift_base + y))
+static int exclusive_scan(Context* ctx, const uint32_t* d_in, size_t n, uint32_t* d_out, uint32_t* d_out_copy, cudaStream_t st,
+                          unsigned rows = 1, unsigned shift_base = 0)
 {
     unsigned tiles = div_up(n, SCAN_TILE);
     if (tiles > SCAN_TILE) {
         set_last_error("scan too large");
         return BBG_ERR_ARG;
     }
-    int rc = ctx->msm_scan_tmp.reserve((size_t)tiles * 4 + 16);
+    int rc = ctx->msm_scan_tmp.reserve((size_t)rows * SCAN_TILE * 4 + 16);
     if (rc) return rc;
     uint32_t* tmp = (uint32_t*)ctx->msm_scan_tmp.p;
-    k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(d_in, n, tmp);
-    k_scan_top<<<1, SCAN_THREADS, 0, st>>>(tmp, tiles);
-    k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(d_in, n, tmp, d_out, d_out_copy);
+    k_scan_tile_sums<<<dim3(tiles, rows), SCAN_THREADS, 0, st>>>(d_in, n, tmp, shift_base);
+    k_scan_top<<<dim3(1, rows), SCAN_THREADS, 0, st>>>(tmp, tiles);
+    k_scan_apply<<<dim3(tiles, rows), SCAN_THREADS, 0, st>>>(d_in, n, tmp, d_out, d_out_copy, shift_base);
     ctx->launches += 3;
     return BBG_OK;
 }
@@ -673,6 +963,24 @@ static unsigned floor_log2(size_t n)
     unsigned lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) ++lg;
     return lg;
+}
+
+// C_k table of inv.cuh for fq, built once per context
+static int ensure_inv_fix(Context* ctx)
+{
+    if (ctx->inv_fix_fq != nullptr) return BBG_OK;
+    uint32_t p[8], r2[8];
+    for (int i = 0; i < 8; ++i) {
+        p[i] = FqParams::P(i);
+        r2[i] = FqParams::R2(i);
+    }
+    std::vector<uint32_t> tab((size_t)inv::FIX_ENTRIES * 8);
+    inv::inv_fix_table(p, r2, tab.data());
+    void* d = nullptr;
+    BBG_CUDA(cudaMalloc(&d, tab.size() * 4));
+    BBG_CUDA(cudaMemcpy(d, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    ctx->inv_fix_fq = d;
+    return BBG_OK;
 }
 
 // window width for an SRS of `n` points when every level is precomputed (bucket reduction is cheap then)
@@ -764,20 +1072,83 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     dp.level_stride = (uint32_t)lv.stride;
     dp.base = (uint32_t)base;
     const unsigned dig_blocks = div_up(n, 256);
-    k_msm_digits<false><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, counts, nullptr);
+    k_msm_digits<DIG_HISTOGRAM><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, counts, nullptr, nullptr, 0, nullptr);
     ctx->launches += 1;
     pr.mark(st, PH_MSM_SCAN);
     if ((rc = exclusive_scan(ctx, counts, G, offsets, cursors, st))) return rc;
+    // ---- optional pairwise affine passes (k_msm_pair_pass): J levels, each halving every bucket's entry count.
+    // OFF by default: measured on B200 (2^20 points, c = 17) the passes take 3.6-4.2 ms against 2.47 ms for the
+    // projective accumulation below -- 5.8 instead of 10 multiplies per addition, but two dependent sweeps over
+    // memory per level and a ~70 us inversion per CTA batch leave the IMAD pipe idle.  Kept as a
+    // tested alternative (BBG_MSM_PAIR_PASSES = number of levels) for parts where the balance differs.
+    unsigned J = env_uint("BBG_MSM_PAIR_PASSES", 0);
+    if (J > 12) J = 12;
+    // optional: the counting sort moves the points themselves (64 B each) so that every later read streams
+    const bool materialise = J > 0 && env_uint("BBG_MSM_MATERIALISE", 0) != 0;
+
     pr.mark(st, PH_MSM_SCATTER);
-    k_msm_digits<true><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, cursors, sorted);
+    affine_t* pts0 = nullptr;
+    if (materialise) {
+        if ((rc = ctx->msm_pts0.reserve(max_entries * sizeof(affine_t)))) return rc;
+        pts0 = (affine_t*)ctx->msm_pts0.p;
+        k_msm_digits<DIG_SCATTER_POINTS><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, cursors, nullptr,
+                                                                      (const affine_t*)d_points, (uint32_t)point_stride, pts0);
+    } else {
+        k_msm_digits<DIG_SCATTER_INDEX><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, cursors, sorted, nullptr, 0, nullptr);
+    }
     ctx->launches += 1;
+
+    const uint32_t* acc_offsets = offsets;
+    const affine_t* acc_points = (const affine_t*)d_points;
+    size_t acc_entries = max_entries;
+    if (J > 0) {
+        if ((rc = ensure_inv_fix(ctx))) return rc;
+        if ((rc = ctx->msm_lvl_offsets.reserve((size_t)J * (G + 1) * 4))) return rc;
+        uint32_t* lvl = (uint32_t*)ctx->msm_lvl_offsets.p; // row j-1: offsets of level j
+        if ((rc = exclusive_scan(ctx, counts, G, lvl, nullptr, st, J, 1))) return rc;
+        // worst-case entry counts per level: sum_b ceil(m_b / 2) <= (E + G) / 2
+        size_t e_max[13];
+        e_max[0] = max_entries;
+        for (unsigned j = 1; j <= J; ++j) e_max[j] = std::min(e_max[j - 1], (e_max[j - 1] + G + 1) / 2);
+        if ((rc = ctx->msm_pairs_a.reserve(e_max[1] * sizeof(affine_t)))) return rc;
+        if (J > 1 && (rc = ctx->msm_pairs_b.reserve(e_max[2] * sizeof(affine_t)))) return rc;
+        if ((rc = ctx->msm_pair_pre.reserve(e_max[1] * 32))) return rc;
+        if ((rc = ctx->msm_pair_meta.reserve(e_max[1] * 8))) return rc;
+        const unsigned k_force = std::min<unsigned>(PAIR_K_MAX, env_uint("BBG_MSM_PAIR_K", 0)); // 0: choose per level
+        pr.mark(st, PH_MSM_PAIRS);
+        const affine_t* in = pts0;
+        const uint32_t* off_in = offsets;
+        for (unsigned j = 1; j <= J; ++j) {
+            affine_t* out = (affine_t*)((j & 1) ? ctx->msm_pairs_a.p : ctx->msm_pairs_b.p);
+            const uint32_t* off_out = lvl + (size_t)(j - 1) * (G + 1);
+            // slots per thread: as many as amortise the inversion, but keep >= ~4 CTAs per SM in the grid
+            unsigned K = (unsigned)(e_max[j] / ((size_t)PAIR_THREADS * ctx->num_sms * 4));
+            K = k_force ? k_force : std::max(4u, std::min(32u, K));
+            const unsigned blocks = div_up(e_max[j], (size_t)PAIR_THREADS * K);
+            if (j == 1 && !materialise) {
+                k_msm_pair_pass<true><<<blocks, PAIR_THREADS, 0, st>>>(
+                    sorted, (const affine_t*)d_points, (uint32_t)point_stride, off_in, off_out, (uint32_t)G, out,
+                    (const uint32_t*)ctx->inv_fix_fq, K, (uint4*)ctx->msm_pair_pre.p, (uint2*)ctx->msm_pair_meta.p);
+            } else {
+                k_msm_pair_pass<false><<<blocks, PAIR_THREADS, 0, st>>>(nullptr, in, 1, off_in, off_out, (uint32_t)G, out,
+                                                                        (const uint32_t*)ctx->inv_fix_fq, K,
+                                                                        (uint4*)ctx->msm_pair_pre.p, (uint2*)ctx->msm_pair_meta.p);
+            }
+            ctx->launches += 1;
+            in = out;
+            off_in = off_out;
+        }
+        acc_offsets = off_in;
+        acc_points = in;
+        acc_entries = e_max[J];
+    }
 
     // chunking: equal work per thread; about two waves of resident threads, chunk >= 16 entries.
     // The number of non-zero digits is only known on the device; size for the maximum.
     const size_t resident = (size_t)ctx->num_sms * ACC_THREADS * 4;
-    size_t chunk = (max_entries + 2 * resident - 1) / (2 * resident);
+    size_t chunk = (acc_entries + 2 * resident - 1) / (2 * resident);
     if (chunk < 16) chunk = 16;
-    const size_t num_chunks = (max_entries + chunk - 1) / chunk;
+    const size_t num_chunks = (acc_entries + chunk - 1) / chunk;
     // slot arrays of all merge levels, back to back
     size_t slots_total = 2 * num_chunks;
     {
@@ -793,9 +1164,14 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     Slot* slots = (Slot*)ctx->msm_partials.p;
 
     pr.mark(st, PH_MSM_ACCUMULATE);
-    k_msm_accumulate<<<div_up(num_chunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
-        sorted, offsets, (uint32_t)G, (uint32_t)chunk, (uint32_t)num_chunks, (const affine_t*)d_points, (uint32_t)point_stride,
-        buckets, slots, pending);
+    if (J > 0) {
+        k_msm_accumulate<true><<<div_up(num_chunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
+            nullptr, acc_offsets, (uint32_t)G, (uint32_t)chunk, (uint32_t)num_chunks, acc_points, 1, buckets, slots, pending);
+    } else {
+        k_msm_accumulate<false><<<div_up(num_chunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
+            sorted, offsets, (uint32_t)G, (uint32_t)chunk, (uint32_t)num_chunks, (const affine_t*)d_points, (uint32_t)point_stride,
+            buckets, slots, pending);
+    }
     ctx->launches += 1;
     pr.mark(st, PH_MSM_FIXUP);
     {

@@ -99,7 +99,7 @@ lib.bbg_set_auto_adopt.argtypes = [_int]
 lib.bbg_bench_field_mul.argtypes = [_int, _int, _vp]
 lib.bbg_g1_add_affine_dev.argtypes = [_vp, _vp, _sz, _vp, _vp]
 NUM_PHASES = 12
-PHASE_NAMES = ["msm_digits", "msm_scan", "msm_scatter", "msm_accumulate", "msm_fixup", "msm_reduce", "msm_combine",
+PHASE_NAMES = ["msm_digits", "msm_scan", "msm_scatter", "msm_pairs", "msm_accumulate", "msm_fixup", "msm_reduce", "msm_combine",
                "ntt_tables", "ntt_pass0", "ntt_pass1", "ntt_pass2", "ntt_pass3"]
 
 

@@ -204,6 +204,54 @@ def test_msm_skewed_buckets(bbg, orc, srs_mini):
     assert orc.jac_to_buffer(bbg.msm_points(sc, pts[:n])) == orc.jac_to_buffer(orc.pippenger(sc, table, n=n, stride=2))
 
 
+@pytest.mark.parametrize("passes,c,k,mat", [(1, 0, 0, 1), (2, 6, 1, 0), (3, 0, 7, 1), (6, 5, 32, 0), (12, 4, 64, 1)])
+def test_msm_pairwise_affine_passes(bbg, orc, srs_mini, passes, c, k, mat, monkeypatch):
+    """Batched-affine bucket accumulation (msm.cu k_msm_pair_pass: pairwise affine additions sharing one Kaliski
+    inversion per CTA batch, the GPU counterpart of scalar_multiplication.cpp:273-401, :523-718).  Large MSMs take
+    this path by themselves; here it is forced on the 4096-point SRS for every number of levels, including more
+    levels than any bucket needs, on uniform, skewed, repeated-point (doubling), cancelling and infinite inputs."""
+    pts, table = srs_mini
+    monkeypatch.setenv("BBG_MSM_PAIR_PASSES", str(passes))
+    monkeypatch.setenv("BBG_MSM_MATERIALISE", str(mat))  # 1: the counting sort moves the points; 0: schedule words + gather
+    if k:
+        monkeypatch.setenv("BBG_MSM_PAIR_K", str(k))  # output slots per thread (default: chosen per level)
+    if c:
+        monkeypatch.setenv("BBG_MSM_C", str(c))
+        monkeypatch.setenv("BBG_MSM_C1", str(c))
+    pip = bbg.Pippenger.from_points(pts)
+    inf_buf = orc.jac_to_buffer(orc.g1_infinity())
+    for n in (4096, 3000, 33, 2, 1):
+        sc = inputs.fr_elements(1200 + n + passes, n, coarse_fraction=0.2)
+        exp = orc.jac_to_buffer(orc.pippenger(sc, pts[:n], stride=1))
+        assert orc.jac_to_buffer(pip.pippenger_unsafe(sc, 0, n)) == exp, n
+        assert orc.jac_to_buffer(bbg.msm_points(sc, pts[:n])) == exp, n
+    # one bucket per window holds everything
+    n = 4096
+    one = np.repeat(inputs.fr_elements(5, 1), n, axis=0)
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(one, 0, n)) == orc.jac_to_buffer(orc.pippenger(one, pts[:n], stride=1))
+    # the same point 64 times: every pairwise addition is a doubling
+    rep = np.zeros((64, 8), dtype=np.uint64)
+    rep[:] = pts[7]
+    sc = inputs.fr_elements(77, 64)
+    same = np.repeat(sc[:1], 64, axis=0)
+    tot = orc.field_op(po.FR, po.OP_MUL, orc.to_mont(po.FR, [64]), same[:1])  # 64 * s
+    assert orc.jac_to_buffer(bbg.msm_points(same, rep)) == orc.jac_to_buffer(orc.g1_mul(pts[7], tot[0]))
+    assert orc.jac_to_buffer(bbg.msm_points(sc, rep)) == orc.jac_to_buffer(orc.pippenger(sc, rep, stride=1))
+    # P and -P with equal scalars meet in the same buckets and cancel; an infinite input is skipped
+    q = np.stack([pts[9], pts[9], pts[11], pts[12]])
+    q[1, 4:] = orc.field_op(po.FQ, po.OP_NEG, pts[9][4:].reshape(1, 4))[0]
+    s4 = np.stack([sc[0], sc[0], sc[1], sc[2]])
+    exp = orc.pippenger(s4[2:], q[2:], stride=1)
+    assert orc.jac_to_buffer(bbg.msm_points(s4, q)) == orc.jac_to_buffer(exp)
+    assert orc.jac_to_buffer(bbg.msm_points(s4[:2], q[:2])) == inf_buf
+    p = pts[:64].copy()
+    p[5, 3] |= np.uint64(1 << 63)
+    s64 = inputs.fr_elements(4, 64)
+    exp = orc.pippenger(np.delete(s64, 5, axis=0), np.delete(pts[:64], 5, axis=0), stride=1)
+    assert orc.jac_to_buffer(bbg.msm_points(s64, p)) == orc.jac_to_buffer(exp)
+    assert orc.jac_to_buffer(bbg.msm_points(np.zeros((100, 4), np.uint64), pts[:100])) == inf_buf
+
+
 # ------------------------------------------------------------------------------------------ NTT
 def test_ntt_golden(bbg, golden, orc):
     for e in golden["ntt"]:
@@ -275,7 +323,7 @@ def test_launch_counter_moves(bbg):
     assert bbg.kernel_launches() > before
 
 
-@pytest.mark.parametrize("levels,c", [(1, 0), (2, 0), (5, 7), (0, 0), (0, 11)])
+@pytest.mark.parametrize("levels,c", [(1, 0), (2, 0), (5, 7), (0, 0), (0, 11), (0, 12), (4, 13), (0, 16)])
 def test_msm_fixed_base_levels(bbg, orc, srs_mini, levels, c, monkeypatch):
     """The Pippenger object's precomputed levels 2^(D l) * P_i (msm.cu k_msm_precompute): every split of the
     windows into levels x bucket sets must give the same group element, for sub-ranges too."""
