@@ -564,6 +564,8 @@ void bbg_delete_pippenger(void* pippenger)
 
 size_t bbg_pippenger_num_points(void* pippenger) { return pippenger ? reinterpret_cast<PippengerObj*>(pippenger)->n : 0; }
 const void* bbg_pippenger_device_points(void* pippenger) { return pippenger ? reinterpret_cast<PippengerObj*>(pippenger)->d_points : nullptr; }
+unsigned bbg_pippenger_window_bits(void* pippenger) { return pippenger ? reinterpret_cast<PippengerObj*>(pippenger)->lv.c : 0; }
+unsigned bbg_pippenger_levels(void* pippenger) { return pippenger ? reinterpret_cast<PippengerObj*>(pippenger)->lv.L : 0; }
 
 int bbg_pippenger_get_point_table(void* pippenger, void* table2n_out)
 {

@@ -50,6 +50,7 @@ struct DigitParams {
     uint32_t B;            // buckets per set = 2^(c-1)
     uint32_t level_stride; // table entries between consecutive levels
     uint32_t base;         // table entry of scalar 0 (Pippenger `from`)
+    uint32_t agg_from;     // windows >= agg_from are narrow (few distinct digits): warp-aggregated counter updates
 };
 
 // MODE 0: histogram of bucket sizes.  MODE 1: counting-sort scatter of schedule words (table index << 1 | negate).
@@ -65,12 +66,13 @@ __global__ void __launch_bounds__(256) k_msm_digits(const fr_t* __restrict__ sca
                                                     uint32_t point_stride,
                                                     affine_t* __restrict__ pts_out)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) {
-        return;
-    }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // no early exit: every lane of a warp walks the (uniform) window loop so that the aggregated path below can name
+    // the full warp in its *_sync primitives; lanes past the end carry an all-zero scalar and never touch memory
+    const bool valid = i < P.n;
     // from_montgomery_form => canonical integer in [0, r)  (scalar_multiplication.cpp:224)
-    fr_t s = fe_from_mont(fe_load_nc<FrParams>(scalars + i));
+    fr_t s = fe_zero<FrParams>();
+    if (valid) s = fe_from_mont(fe_load_nc<FrParams>(scalars + i));
     uint32_t k[9];
 #pragma unroll
     for (int j = 0; j < 8; ++j) k[j] = s.l[j];
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const fr_t* __restrict__ sca
     const uint32_t c = P.c;
     const uint32_t half = 1u << (c - 1);
     const uint32_t mask = (1u << c) - 1;
+    const unsigned lane = threadIdx.x & 31;
     uint32_t carry = 0;
     uint32_t level = 0, set = 0;
     for (unsigned w = 0; w < P.W; ++w) {
@@ -95,21 +98,31 @@ __global__ void __launch_bounds__(256) k_msm_digits(const fr_t* __restrict__ sca
         uint32_t neg = v > half ? 1u : 0u;
         uint32_t mag = neg ? (mask + 1 - v) : v;
         carry = neg;
-        if (mag) {
-            uint32_t g = set * P.B + (mag - 1);
+        const bool live = valid && mag != 0;
+        const uint32_t g = set * P.B + (mag - 1);
+        uint32_t dst = 0;
+        if (w >= P.agg_from) {
+            // The top window of a 254-bit scalar can be a few bits wide (c = 18: two bits): a million atomics on
+            // three addresses serialise in L2.  One atomic per distinct bucket per warp instead.
+            const unsigned peers = __match_any_sync(0xffffffffu, live ? g : 0xffffffffu);
+            const int leader = __ffs(peers) - 1;
+            uint32_t first = 0;
+            if (live && (int)lane == leader) first = atomicAdd(&counters[g], (uint32_t)__popc(peers));
+            first = __shfl_sync(0xffffffffu, first, leader);
+            dst = first + __popc(peers & ((1u << lane) - 1u));
+        } else if (live) {
+            dst = atomicAdd(&counters[g], 1u);
+        }
+        if (live) {
             if (MODE == DIG_SCATTER_INDEX) {
-                uint32_t dst = atomicAdd(&counters[g], 1u);
                 sorted[dst] = ((level * P.level_stride + P.base + i) << 1) | neg;
             } else if (MODE == DIG_SCATTER_POINTS) {
                 // (re)load per window: with fixed-base levels every window has its own point; with L == 1 the
                 // reload hits L1
                 affine_t pt = affine_load(points + (size_t)(level * P.level_stride + P.base + i) * point_stride);
                 if (neg) pt.y = fe_neg(pt.y);
-                uint32_t dst = atomicAdd(&counters[g], 1u);
                 fe_store(&pts_out[dst].x, pt.x);
                 fe_store(&pts_out[dst].y, pt.y);
-            } else {
-                atomicAdd(&counters[g], 1u);
             }
         }
         if (++set == P.S) {
@@ -684,27 +697,42 @@ __global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
 // ------------------------------------------------------------------------------------------------
 // 5. bucket reduction: sum over b of (b + 1) * bucket[b] per set
 // ------------------------------------------------------------------------------------------------
-// Worker (set, seg): running sums over buckets [seg*ell, (seg+1)*ell):  R = sum x_j,  A = sum (j+1) x_j,
-// then V = A + (seg*ell) * R by double-and-add.  One add site: the loop alternates run += x / acc += run.
-__global__ void __launch_bounds__(128) k_msm_segments(const xyzz_t* __restrict__ buckets,
-                                                       uint32_t B,   // buckets per set
-                                                       uint32_t ell, // segment length (divides B)
+// Two levels of running sums.  Cut the B items of a set into segments of `ell0`:  with T_t = sum of segment t and
+// R_t = sum_j (j + 1) x_{t ell0 + j} (both fall out of one running-sum sweep, 2 ell0 additions),
+//     sum_b (b + 1) x_b  =  sum_t R_t  +  ell0 * sum_{t >= 1} t T_t,
+// and the last term is the SAME problem on the array T[1..] (weights 1, 2, ...), a factor ell0 smaller.  Level 0
+// (k_msm_segments<false>) is the throughput-bound sweep over all buckets; level 1 (k_msm_segments<true>) works on
+// T[1..] and finishes each segment with the double-and-add by its offset, which is now paid by B / (ell0 ell1)
+// workers instead of B / ell.  Everything here is latency bound (one lone-warp g1 addition is ~4.5 us), so the
+// design minimises the serial chain: 2 ell0 + 2 ell1 + log2(B / ell0) additions/doublings, then one batched tree
+// sum over both levels and a 3-doubling Horner step in k_msm_finish.
+// Worker (set, seg): items [seg*ell, min((seg+1)*ell, count)) of in + set*in_stride.  One add site: the loop
+// alternates run += x / acc += run.
+template <bool OFFSET>
+__global__ void __launch_bounds__(128, 4) k_msm_segments(const xyzz_t* __restrict__ in,
+                                                       uint32_t in_stride, // items between consecutive sets
+                                                       uint32_t count,     // items per set
+                                                       uint32_t ell,       // segment length
+                                                       uint32_t segs,      // segments per set = ceil(count / ell)
                                                        uint32_t num_workers,
-                                                       xyzz_t* __restrict__ out)
+                                                       xyzz_t* __restrict__ out_r,
+                                                       xyzz_t* __restrict__ out_t)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= num_workers) {
         return;
     }
-    const uint32_t segs = B / ell;
     const uint32_t set = t / segs, seg = t % segs;
-    const xyzz_t* src = buckets + (size_t)set * B + (size_t)seg * ell;
+    const xyzz_t* src = in + (size_t)set * in_stride;
+    const uint32_t first = seg * ell;
     xyzz_t run = xyzz_infinity(), acc = xyzz_infinity();
     for (uint32_t step = 0; step < 2 * ell; ++step) {
         const bool second = step & 1;
         xyzz_t rhs;
         if (!second) {
-            rhs = xyzz_load(src + (ell - 1 - (step >> 1)));
+            const uint32_t idx = first + (ell - 1 - (step >> 1));
+            rhs = xyzz_infinity();
+            if (idx < count) rhs = xyzz_load(src + idx);
         } else {
             rhs = run;
         }
@@ -716,61 +744,86 @@ __global__ void __launch_bounds__(128) k_msm_segments(const xyzz_t* __restrict__
             run = lhs;
         }
     }
-    // V = acc + (seg * ell) * run
-    const uint32_t k = seg * ell;
-    if (k != 0 && !xyzz_is_inf(run)) {
-        const int msb = 31 - __clz(k);
-        xyzz_t m = run;
-        for (int bit = msb - 1; bit >= -1; --bit) {
-            xyzz_t rhs;
-            bool do_add;
-            if (bit >= 0) {
-                m = xyzz_dbl(m);
-                rhs = run;
-                do_add = (k >> bit) & 1;
-            } else {
-                rhs = acc; // last step: fold in A
-                do_add = true;
+    if (OFFSET) {
+        // V = acc + first * run by double-and-add
+        const uint32_t k = first;
+        if (k != 0 && !xyzz_is_inf(run)) {
+            const int msb = 31 - __clz(k);
+            xyzz_t m = run;
+            for (int bit = msb - 1; bit >= -1; --bit) {
+                xyzz_t rhs;
+                bool do_add;
+                if (bit >= 0) {
+                    m = xyzz_dbl(m);
+                    rhs = run;
+                    do_add = (k >> bit) & 1;
+                } else {
+                    rhs = acc; // last step: fold in A
+                    do_add = true;
+                }
+                if (do_add) {
+                    xyzz_add(m, rhs);
+                }
             }
-            if (do_add) {
-                xyzz_add(m, rhs);
-            }
+            acc = m;
         }
-        acc = m;
+        xyzz_store(out_r + t, acc);
+    } else {
+        xyzz_store(out_r + t, acc);
+        xyzz_store(out_t + t, run);
     }
-    xyzz_store(out + t, acc);
 }
 
-// Sum of m consecutive XYZZ points per row: grid (parts, rows); each CTA strides over its share and
-// finishes with a warp-shuffle tree + one shared-memory hop.  out[row * parts + part].
+// Rows of the batched tree sum: row = level * S + set; level `l` has m[l] entries per set starting at off[l].
+static constexpr int REDUCE_MAX_LEVELS = 24;
+struct ReduceRows {
+    uint32_t S;
+    uint32_t levels;
+    uint32_t off[REDUCE_MAX_LEVELS]; // entry offset of level l's R array (set-major, m[l] per set)
+    uint32_t m[REDUCE_MAX_LEVELS];
+    uint32_t shift[REDUCE_MAX_LEVELS]; // log2(ell) of level l
+};
+
+// Sum of the XYZZ points of every row: grid (parts, rows); each CTA strides over its share and finishes with a
+// warp-shuffle tree + one shared-memory hop.  out[row * parts + part].  A CTA whose share is empty stores infinity.
 static constexpr int TREE_THREADS = 256;
-__global__ void __launch_bounds__(TREE_THREADS) k_msm_tree_sum(const xyzz_t* __restrict__ in, uint32_t m, xyzz_t* __restrict__ out)
+__global__ void __launch_bounds__(TREE_THREADS) k_msm_tree_sum(const xyzz_t* __restrict__ in, const ReduceRows rows, xyzz_t* __restrict__ out)
 {
     __shared__ xyzz_t sm[TREE_THREADS / 32];
     const uint32_t parts = gridDim.x, part = blockIdx.x, row = blockIdx.y;
-    const xyzz_t* src = in + (size_t)row * m;
+    const uint32_t level = row / rows.S, set = row % rows.S;
+    const uint32_t m = rows.m[level];
+    const xyzz_t* src = in + rows.off[level] + (size_t)set * m;
     const uint32_t per = (m + parts - 1) / parts;
     const uint32_t lo = part * per;
     const uint32_t hi = min(lo + per, m);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lo >= hi) { // uniform per CTA
+        if (threadIdx.x == 0) xyzz_store(out + (size_t)row * parts + part, xyzz_infinity());
+        return;
+    }
 
     xyzz_t acc = xyzz_infinity();
     const uint32_t iters = (per + TREE_THREADS - 1) / TREE_THREADS;
-    // steps [0, iters): strided loads; next 5: shuffle tree inside each warp; last 5: warp 0 folds the warp sums
-    for (uint32_t step = 0; step < iters + 10; ++step) {
+    // steps [0, iters): strided loads; next 5: shuffle tree inside each warp; last 3: warp 0 folds the 8 warp sums
+    // (every addition is ~4.5 us of serial latency here, so the chain is kept as short as the shape allows)
+    for (uint32_t step = 0; step < iters + 8; ++step) {
         xyzz_t rhs = xyzz_infinity();
         if (step < iters) {
             const uint32_t i = lo + step * TREE_THREADS + threadIdx.x;
             if (i < hi) rhs = xyzz_load(src + i);
         } else {
-            const uint32_t s = (step - iters) % 5;
-            if (step == iters + 5) {
-                if (lane == 0) sm[warp] = acc;
-                __syncthreads();
-                acc = (warp == 0 && lane < TREE_THREADS / 32) ? sm[lane] : xyzz_infinity();
+            uint32_t delta = 16u >> (step - iters);
+            if (step >= iters + 5) {
+                if (step == iters + 5) {
+                    if (lane == 0) sm[warp] = acc;
+                    __syncthreads();
+                    acc = (warp == 0 && lane < TREE_THREADS / 32) ? sm[lane] : xyzz_infinity();
+                }
+                delta = 4u >> (step - iters - 5);
             }
-            rhs = xyzz_shfl_down(acc, 16 >> s);
-            if (lane + (16 >> s) >= 32) rhs = xyzz_infinity();
+            rhs = xyzz_shfl_down(acc, (int)delta);
+            if (lane + delta >= 32) rhs = xyzz_infinity();
         }
         xyzz_add(acc, rhs);
     }
@@ -779,9 +832,27 @@ __global__ void __launch_bounds__(TREE_THREADS) k_msm_tree_sum(const xyzz_t* __r
     }
 }
 
-// 6. result = sum_r 2^(c r) * set_sum[r], XYZZ -> Jacobian
-__global__ void __launch_bounds__(32) k_msm_finish(const xyzz_t* __restrict__ set_sums, uint32_t S, uint32_t c, jac_t* __restrict__ out)
+// 6. per set: V = R_0 + ell_0 (R_1 + ell_1 (R_2 + ...)) (one thread per set), then
+//    result = sum_r 2^(c r) * V[r] (thread 0), XYZZ -> Jacobian.  level_sums[level * S + set].
+static constexpr int FINISH_THREADS = 256; // >= max number of bucket sets (windows): c >= 1 => W <= 255
+__global__ void __launch_bounds__(FINISH_THREADS) k_msm_finish(const xyzz_t* __restrict__ level_sums, const ReduceRows rows, uint32_t c,
+                                                               jac_t* __restrict__ out)
 {
+    __shared__ xyzz_t sm[FINISH_THREADS];
+    const uint32_t S = rows.S;
+    if (threadIdx.x < S) {
+        // Horner from the deepest level; one add site and one doubling site
+        xyzz_t v = xyzz_infinity();
+        for (int level = (int)rows.levels - 1; level >= 0; --level) {
+            for (uint32_t d = 0; d < rows.shift[level] && level != (int)rows.levels - 1; ++d) {
+                v = xyzz_dbl(v);
+            }
+            xyzz_t r = xyzz_load(level_sums + (size_t)level * S + threadIdx.x);
+            xyzz_add(v, r);
+        }
+        sm[threadIdx.x] = v;
+    }
+    __syncthreads();
     if (threadIdx.x != 0) {
         return;
     }
@@ -792,7 +863,7 @@ __global__ void __launch_bounds__(32) k_msm_finish(const xyzz_t* __restrict__ se
                 acc = xyzz_dbl(acc);
             }
         }
-        xyzz_t s = xyzz_load(set_sums + r);
+        xyzz_t s = sm[r];
         xyzz_add(acc, s);
     }
     jac_t j = xyzz_to_jacobian(acc);
@@ -983,12 +1054,22 @@ static int ensure_inv_fix(Context* ctx)
     return BBG_OK;
 }
 
-// window width for an SRS of `n` points when every level is precomputed (bucket reduction is cheap then)
+// window width for an SRS of `n` points when every level is precomputed (one bucket set of 2^(c-1) buckets).
+// Cost model: W(c) n mixed additions (10 mul each, throughput bound) + a bucket reduction whose cost is ~60 serial g1
+// additions of latency plus 2 full additions per bucket.  Widths whose TOP window holds only a few scalar bits
+// (c = 14, 18, 19: 254 - (W - 1) c = 2, 2, 7) are skipped: that window's n digits fall into a handful of buckets,
+// which the equal-chunk accumulation handles correctly but pays for in merge levels.
+// Measured on B200 (ms per MSM, uniform scalars):  n = 2^16: c 14 1.03, 15 0.82, 16 0.78;  2^18: c 16 1.40, 17 1.30,
+// 18 1.54;  2^20: c 16 3.65, 17 3.37, 18 3.61, 19 3.71, 20 3.27;  2^23: c 20 20.2.
 static unsigned msm_window_bits(size_t n)
 {
-    int c = (int)floor_log2(n ? n : 1) - 4;
-    if (c < 4) c = 4;
-    if (c > 20) c = 20;
+    const int lg = (int)floor_log2(n ? n : 1);
+    int c;
+    if (lg >= 20) c = 20;
+    else if (lg >= 17) c = 17;
+    else if (lg >= 15) c = 16;
+    else if (lg >= 13) c = 15;
+    else c = 13;
     return env_uint("BBG_MSM_C", (unsigned)c);
 }
 
@@ -1071,6 +1152,15 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     dp.B = B;
     dp.level_stride = (uint32_t)lv.stride;
     dp.base = (uint32_t)base;
+    // windows that hold fewer than ~10 scalar bits (+1 for the signed-digit carry) collide in a handful of buckets
+    dp.agg_from = W;
+    for (unsigned w = 0; w < W; ++w) {
+        if (w * c + 10 >= 254) {
+            dp.agg_from = w;
+            break;
+        }
+    }
+    dp.agg_from = env_uint("BBG_MSM_AGG_FROM", dp.agg_from);
     const unsigned dig_blocks = div_up(n, 256);
     k_msm_digits<DIG_HISTOGRAM><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, counts, nullptr, nullptr, 0, nullptr);
     ctx->launches += 1;
@@ -1191,30 +1281,63 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
         }
     }
 
-    // bucket reduction
+    // bucket reduction (see the comment above k_msm_segments)
     pr.mark(st, PH_MSM_REDUCE);
-    uint32_t ell = 16;
-    while (ell > 1 && (G / ell) < 8192) ell >>= 1; // keep at least ~8K workers in flight
-    if (ell > B) ell = B;
-    const uint32_t segs = B / ell;
-    const uint32_t workers = segs * S;
-    const uint32_t parts = std::min<uint32_t>(64, std::max<uint32_t>(1, segs / 64));
-    if ((rc = ctx->msm_reduce.reserve(((size_t)workers + (size_t)S * parts + S) * sizeof(xyzz_t)))) return rc;
-    xyzz_t* seg_out = (xyzz_t*)ctx->msm_reduce.p;
-    xyzz_t* part_out = seg_out + workers;
-    xyzz_t* set_out = part_out + (size_t)S * parts;
-    k_msm_segments<<<div_up(workers, 128), 128, 0, st>>>(buckets, B, ell, workers, seg_out);
-    k_msm_tree_sum<<<dim3(parts, S), TREE_THREADS, 0, st>>>(seg_out, segs, part_out);
-    ctx->launches += 2;
-    const xyzz_t* sums = part_out;
-    if (parts > 1) {
-        k_msm_tree_sum<<<dim3(1, S), TREE_THREADS, 0, st>>>(part_out, parts, set_out);
+    {
+        const unsigned sh0 = std::min(6u, env_uint("BBG_MSM_ELL0_LOG2", B >= (1u << 18) ? 4u : 2u));
+        const unsigned sh1 = std::min(6u, env_uint("BBG_MSM_ELL1_LOG2", 2u));
+        ReduceRows rows;
+        memset(&rows, 0, sizeof(rows));
+        rows.S = (uint32_t)S;
+        const uint32_t segs0 = (B + (1u << sh0) - 1) >> sh0;
+        const uint32_t count1 = segs0 - 1; // level 1 works on T[1..]
+        const uint32_t segs1 = (count1 + (1u << sh1) - 1) >> sh1;
+        rows.levels = count1 ? 2 : 1;
+        rows.shift[0] = sh0;
+        rows.m[0] = segs0;
+        rows.off[0] = 0;
+        rows.shift[1] = sh1;
+        rows.m[1] = segs1;
+        rows.off[1] = (uint32_t)((size_t)segs0 * S);
+        const size_t total_segs = (size_t)segs0 + segs1;
+        const unsigned levels = rows.levels;
+        // parts: every first-stage CTA sums <= 2 entries per thread, the second stage <= 2 per thread as well
+        const uint32_t parts = std::min<uint32_t>(2 * TREE_THREADS, std::max<uint32_t>(1, segs0 / (2 * TREE_THREADS)));
+        const size_t n_rows = (size_t)levels * S;
+        // layout: R0 | V1 | T0 | per-part sums | per-row sums
+        if ((rc = ctx->msm_reduce.reserve(((total_segs + segs0) * S + n_rows * parts + n_rows) * sizeof(xyzz_t)))) return rc;
+        xyzz_t* r_all = (xyzz_t*)ctx->msm_reduce.p;
+        xyzz_t* t0 = r_all + total_segs * S;
+        xyzz_t* part_out = t0 + (size_t)segs0 * S;
+        xyzz_t* row_out = part_out + n_rows * parts;
+        {
+            const uint32_t workers = segs0 * (uint32_t)S;
+            k_msm_segments<false><<<div_up(workers, 128), 128, 0, st>>>(buckets, B, B, 1u << sh0, segs0, workers, r_all, t0);
+            ctx->launches += 1;
+        }
+        if (count1) {
+            const uint32_t workers = segs1 * (uint32_t)S;
+            k_msm_segments<true><<<div_up(workers, 128), 128, 0, st>>>(t0 + 1, segs0, count1, 1u << sh1, segs1, workers,
+                                                                       r_all + rows.off[1], nullptr);
+            ctx->launches += 1;
+        }
+        k_msm_tree_sum<<<dim3(parts, (unsigned)n_rows), TREE_THREADS, 0, st>>>(r_all, rows, part_out);
         ctx->launches += 1;
-        sums = set_out;
+        const xyzz_t* sums = part_out;
+        if (parts > 1) {
+            ReduceRows second;
+            memset(&second, 0, sizeof(second));
+            second.S = (uint32_t)n_rows; // every row of the first stage is one "set" of a single level with `parts` entries
+            second.levels = 1;
+            second.m[0] = parts;
+            k_msm_tree_sum<<<dim3(1, (unsigned)n_rows), TREE_THREADS, 0, st>>>(part_out, second, row_out);
+            ctx->launches += 1;
+            sums = row_out;
+        }
+        pr.mark(st, PH_MSM_COMBINE);
+        k_msm_finish<<<1, FINISH_THREADS, 0, st>>>(sums, rows, c, (jac_t*)d_out);
+        ctx->launches += 1;
     }
-    pr.mark(st, PH_MSM_COMBINE);
-    k_msm_finish<<<1, 32, 0, st>>>(sums, S, c, (jac_t*)d_out);
-    ctx->launches += 1;
     pr.mark(st, -1);
     BBG_CUDA(cudaGetLastError());
     return BBG_OK;

@@ -29,7 +29,7 @@ EXPORTS = [
     "bbg_ntt_dist_layout", "bbg_ntt_dist_dev", "bbg_pippenger_bind_host_table", "bbg_set_auto_adopt", "bbg_bench_field_mul", "bbg_g1_add_affine_dev", "bbg_profile", "bbg_profile_read", "bbg_init", "bbg_shutdown", "bbg_last_error", "bbg_device_count", "bbg_kernel_launches", "bbg_last_device_ms",
     "bbg_malloc", "bbg_free", "bbg_new_pippenger", "bbg_new_pippenger_from_path", "bbg_new_pippenger_from_table",
     "bbg_new_pippenger_from_points", "bbg_new_pippenger_from_device_points", "bbg_delete_pippenger", "bbg_pippenger_num_points", "bbg_pippenger_get_point_table",
-    "bbg_pippenger_device_points", "bbg_pippenger_unsafe", "bbg_pippenger_unsafe_dev", "bbg_pippenger", "bbg_msm_points",
+    "bbg_pippenger_device_points", "bbg_pippenger_window_bits", "bbg_pippenger_levels", "bbg_pippenger_unsafe", "bbg_pippenger_unsafe_dev", "bbg_pippenger", "bbg_msm_points",
     "bbg_msm_points_dev", "bbg_generate_pippenger_point_table", "bbg_g1_sum", "bbg_g1_sum_dev", "bbg_read_transcript_g1",
     "bbg_read_g1_elements_from_buffer", "bbg_ntt", "bbg_ntt_dev", "bbg_coset_fft_ext", "bbg_coset_fft_ext_dev",
     "bbg_new_evaluation_domain", "bbg_delete_evaluation_domain", "bbg_ifft", "bbg_coset_fft_with_generator_shift",
@@ -67,6 +67,10 @@ lib.bbg_pippenger_num_points.argtypes = [_vp]
 lib.bbg_pippenger_get_point_table.argtypes = [_vp, _vp]
 lib.bbg_pippenger_device_points.restype = _vp
 lib.bbg_pippenger_device_points.argtypes = [_vp]
+lib.bbg_pippenger_window_bits.restype = ctypes.c_uint
+lib.bbg_pippenger_window_bits.argtypes = [_vp]
+lib.bbg_pippenger_levels.restype = ctypes.c_uint
+lib.bbg_pippenger_levels.argtypes = [_vp]
 lib.bbg_pippenger_unsafe.argtypes = [_vp, _vp, _sz, _sz, _vp]
 lib.bbg_pippenger_unsafe_dev.argtypes = [_vp, _vp, _sz, _sz, _vp, _vp]
 lib.bbg_pippenger.argtypes = [_vp, _vp, _sz, _int, _vp]
@@ -241,6 +245,12 @@ class Pippenger:
 
     def get_num_points(self):
         return int(lib.bbg_pippenger_num_points(self.h))
+
+    def window_bits(self):
+        return int(lib.bbg_pippenger_window_bits(self.h))
+
+    def levels(self):
+        return int(lib.bbg_pippenger_levels(self.h))
 
     def get_point_table(self):
         out = np.zeros((2 * self.get_num_points(), 8), dtype=np.uint64)

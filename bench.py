@@ -67,7 +67,9 @@ def srs_dir_and_capacity():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  The timed region of
+    this bench is tens of milliseconds, far below nvidia-smi's polling period, so the samples come from NVML directly
+    (nvidia_ml_py) on a background thread every ~1 ms; `nvidia-smi -lms` is only the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -75,9 +77,47 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
+        self.thread = None
         self.path = "/tmp/bbg_clocks_%d_%d.csv" % (os.getpid(), index)
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = self.handle
+        bits = []
+        for name, const in (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                            ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")):
+            if hasattr(nv, const):
+                bits.append((name, getattr(nv, const)))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            phys = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            self.handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))]
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -87,6 +127,13 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out = {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+                       "samples": len(self.sm), "source": "nvml"}
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -115,7 +162,7 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
         return out
 
 
@@ -341,7 +388,7 @@ def run_ours(args):
         except Exception:
             traffic = None
     Wn = {k: v / K for k, v in phase_ms.items() if k.startswith("msm")}
-    c_bits = max(4, min(20, args.log_n - 4))
+    c_bits = pip.window_bits()
     windows = (255 + c_bits - 1) // c_bits
     acc_muls = 10.0 * windows * n  # 8M + 2S per mixed addition, one per non-zero digit (upper bound)
     line = {
@@ -361,7 +408,7 @@ def run_ours(args):
         "int_pipe": {"unit": "G fq-mul/s", "peak": fq_muls / 1e9, "peak_source": "bbg_bench_field_mul measured in this run",
                      "achieved": acc_muls / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
                      "frac": (acc_muls / (acc_ms * 1e-3)) / fq_muls if acc_ms > 0 else None, "kernel": "k_msm_accumulate",
-                     "model": "10 fq mul per mixed add x %d windows x n" % windows},
+                     "model": "10 fq mul per mixed add x %d windows (c = %d, %d fixed-base levels) x n" % (windows, c_bits, pip.levels())},
         "phases_ms": Wn,
         "result_x_limb0": int(np.asarray(result).view(np.uint64)[0]),
     }

@@ -82,6 +82,10 @@ void bbg_delete_pippenger(void* pippenger);
 size_t bbg_pippenger_num_points(void* pippenger);
 int bbg_pippenger_get_point_table(void* pippenger, void* table2n_out);
 const void* bbg_pippenger_device_points(void* pippenger); /* n contiguous affine points in HBM */
+/* No reference counterpart (the CPU picks its window in runtime_states.hpp:9-63): the signed-window width c and the
+ * number of precomputed fixed-base levels 2^(c l) P_i this object holds in HBM; reported by bench.py. */
+unsigned bbg_pippenger_window_bits(void* pippenger);
+unsigned bbg_pippenger_levels(void* pippenger);
 
 /* c_bind.cpp:36-43 pippenger_unsafe(pippenger, scalars, from, range, result) ==
  * Pippenger::pippenger_unsafe(scalars, from, range) (pippenger.cpp:27-31): MSM over monomials [from, from+range).
