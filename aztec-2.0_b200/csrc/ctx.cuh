@@ -89,6 +89,16 @@ struct Context {
     // NTT workspaces
     DevBuf ntt_data, ntt_scratch, ntt_pro, ntt_epi, ntt_small;
     std::map<unsigned, void*> ntt_twiddles; // log2n -> w_N^e table (N entries)
+    // full geometric tables T[i] = start * shift^i cached across calls (coset pre/post scalings, 1/n-scaled twiddles):
+    // a key is promoted to a table the second time it is seen, so one-off constants never pay for a build
+    struct ScaleTab {
+        uint64_t count = 0;
+        uint64_t start[4] = {}, shift[4] = {};
+        void* tab = nullptr; // nullptr: key seen once, not built yet
+        uint64_t last_use = 0;
+    };
+    std::vector<ScaleTab> ntt_scale_cache;
+    uint64_t ntt_scale_clock = 0;
     void* ntt_stage_tw[2] = { nullptr, nullptr }; // per-direction small stage-twiddle tables
     // pinned staging for small results
     void* pinned = nullptr;

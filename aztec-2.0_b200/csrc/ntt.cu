@@ -23,16 +23,29 @@
 #include "field.cuh"
 #include "internal.hpp"
 
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 namespace bbg {
 
 using fr = Fe<FrParams>;
 
+// The pass kernel is a template over LOGE: every thread holds E = 2^LOGE elements (radix-E rounds) and a tile is
+// N_p rows x E adjacent columns.  E = 8: 128 registers, 2 CTAs / SM (4 warps per scheduler); E = 4: <= 80 registers,
+// 3 CTAs / SM (6 warps per scheduler) at the price of one more shared-memory exchange per pass.  The passes are
+// bound by dependent IMAD.WIDE chains ("stall_wait" is the top stall reason in the ncu capture), so the extra
+// warps are what raises the pipe utilisation.
 static constexpr int NTT_THREADS = 256;
-static constexpr int NTT_COLS = 8;                       // columns per tile
-static constexpr int NTT_TILE_ELEMS = NTT_THREADS * 8;   // 2048 elements per CTA
-static constexpr int NTT_PAD = 9;                        // row pitch in 16-byte units (8 columns + 1 pad)
-static constexpr int NTT_SMEM_BYTES = 2 * (NTT_TILE_ELEMS / NTT_COLS) * NTT_PAD * 16; // 73,728 B
+template <int LOGE> struct NttGeom {
+    static constexpr int E = 1 << LOGE;                         // elements per thread = columns per tile
+    static constexpr int PAD = E + 1;                           // row pitch in 16-byte units (E columns + 1 pad)
+    static constexpr int HALF_STRIDE = NTT_THREADS * PAD;       // 16-byte units between the two halves of an element
+    static constexpr int SMEM_BYTES = 2 * HALF_STRIDE * 16;     // E = 8: 73,728 B; E = 4: 40,960 B
+    static constexpr int MIN_CTAS = LOGE == 3 ? 2 : 3;
+};
 static constexpr int NTT_MAX_PASSES = 4;
+static constexpr unsigned NTT_DEFAULT_LOGE = 2; // measured at 2^22: fft 0.892 ms with E = 4 vs 0.948 ms with E = 8 (BBG_NTT_LOGE=3)
 
 struct PassParams {
     const fr* src;
@@ -52,10 +65,15 @@ struct PassParams {
     // fused pre-scaling (first pass): x[i] *= pro_hi[i >> split] * pro_lo[i & mask], i < pro_size
     const fr* pro_lo;
     const fr* pro_hi;
+    const fr* pro_full; // cached full table start * shift^i (one multiply instead of two); overrides pro_lo / pro_hi
     uint32_t pro_split;
     uint64_t pro_size;
-    // fused post-scaling (last pass): mode 0 none, 1 constant, 2 epi_hi[o >> split] * epi_lo[o & mask]
+    // fused post-scaling (last pass): mode 0 none, 1 constant, 2 epi_hi[o >> split] * epi_lo[o & mask], 3 epi_full[o]
     uint32_t epi_mode;
+    const fr* epi_full;
+    // non-last pass: inter-pass twiddles taken from a table already multiplied by the final constant (1/n of an
+    // ifft), indexed by the forward exponent; every element is multiplied (entry 0 carries the constant)
+    const fr* tw_scaled;
     const fr* epi_lo;
     const fr* epi_hi;
     uint32_t epi_split;
@@ -111,6 +129,42 @@ __device__ __forceinline__ void bfly_notw(fr& u, fr& v)
     u = s;
 }
 
+// LOGE (or fewer) DIF stages on the E registers x[j], j = LOGE-bit value of row bits [w0, w0 + LOGE).
+// Stages run for row bits b_hi, b_hi-1, ..., w0 (b_hi <= w0 + LOGE - 1). lo = row bits below w0.
+// Stage s (row bit w0 + s) pairs j with j + 2^s; its twiddle exponent is ((j mod 2^s) << w0 | lo) << (g-1-w0-s).
+template <int LOGE>
+__device__ __forceinline__ void radix_round(fr (&x)[1 << LOGE], uint32_t g, uint32_t w0, uint32_t b_hi, uint32_t lo,
+                                            const fr* __restrict__ stage_tw)
+{
+    // In the last round (w0 == 0, hence lo == 0 for every thread) the exponent is zero exactly when
+    // j mod 2^s == 0: those butterflies skip the multiply.  The test is warp-uniform, so nothing diverges.
+    const bool tail = (w0 == 0);
+#pragma unroll
+    for (int s = LOGE - 1; s >= 0; --s) {
+        if (b_hi >= w0 + (uint32_t)s) {
+            const uint32_t sh = g - 1 - w0 - (uint32_t)s;
+#pragma unroll
+            for (int v = 0; v < (1 << s); ++v) {
+                if (tail && v == 0) {
+#pragma unroll
+                    for (int u = 0; u < (1 << (LOGE - 1 - s)); ++u) {
+                        const int j = (u << (s + 1)) | v;
+                        bfly_notw(x[j], x[j + (1 << s)]);
+                    }
+                } else {
+                    const uint32_t e = (((uint32_t)v << w0) | lo) << sh;
+                    fr w = fe_load_nc<FrParams>(stage_tw + e);
+#pragma unroll
+                    for (int u = 0; u < (1 << (LOGE - 1 - s)); ++u) {
+                        const int j = (u << (s + 1)) | v;
+                        bfly(x[j], x[j + (1 << s)], w);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Three (or fewer) DIF stages on the 8 registers x[j], j = 3-bit value of row bits [w0, w0+3).
 // Stages run for row bits b_hi, b_hi-1, ..., w0 (b_hi <= w0 + 2). lo = row bits below w0.
 __device__ __forceinline__ void radix8_round(fr (&x)[8], uint32_t g, uint32_t w0, uint32_t b_hi, uint32_t lo, const fr* __restrict__ stage_tw)
@@ -164,51 +218,62 @@ __device__ __forceinline__ void radix8_round(fr (&x)[8], uint32_t g, uint32_t w0
     }
 }
 
-__global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
+template <> __device__ __forceinline__ void radix_round<3>(fr (&x)[8], uint32_t g, uint32_t w0, uint32_t b_hi, uint32_t lo,
+                                                            const fr* __restrict__ stage_tw)
+{
+    radix8_round(x, g, w0, b_hi, lo, stage_tw); // hand-unrolled form: ptxas spills less with it than with the generic loops
+}
+
+template <int LOGE>
+__global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pass(const PassParams P)
 {
     extern __shared__ uint4 sm[];
-    const uint32_t half_stride = (NTT_TILE_ELEMS / NTT_COLS) * NTT_PAD;
+    constexpr int E = NttGeom<LOGE>::E;
+    constexpr uint32_t NTT_PAD = NttGeom<LOGE>::PAD;
+    const uint32_t half_stride = NttGeom<LOGE>::HALF_STRIDE;
 
     const uint32_t g = P.g;
     const uint32_t R = 1u << g;                   // rows per tile
     const uint32_t tiles_per_cta = NTT_THREADS >> g; // R threads per tile (g <= 8)
     const uint32_t tile_local = threadIdx.x >> g;
     const uint32_t tau = threadIdx.x & (R - 1);
-    const uint32_t col = tau & 7;
-    const uint32_t q = tau >> 3;                  // [0, R/8)
+    const uint32_t col = tau & (E - 1);
+    const uint32_t q = tau >> LOGE;               // [0, R/E)
     const uint64_t N = 1ull << P.tw_log_n;                  // full transform (twiddle exponents)
-    const uint64_t num_tiles = (1ull << P.log_n) >> (g + 3); // local array
+    const uint64_t num_tiles = (1ull << P.log_n) >> (g + LOGE); // local array
     const uint64_t tile = (uint64_t)blockIdx.x * tiles_per_cta + tile_local;
     const bool active = tile < num_tiles;
     const uint32_t sm_base = tile_local * R * NTT_PAD; // this tile's rows inside the CTA's shared memory
-    const uint32_t rows8 = R >> 3;
+    const uint32_t rows8 = R >> LOGE;
 
     // ---- tile coordinates
     uint64_t in_base = 0;     // address of (row 0, col 0)
     uint64_t rest0 = 0;       // non-last: first value of the low index; last: first o_1 of the tile
     uint64_t mid = 0;
     if (!P.last) {
-        const uint64_t chunks = 1ull << (P.below - 3); // column chunks per hi value
+        const uint64_t chunks = 1ull << (P.below - LOGE); // column chunks per hi value
         const uint64_t hi = tile / chunks;
-        rest0 = (tile % chunks) << 3;
+        rest0 = (tile % chunks) << LOGE;
         in_base = (hi << (g + P.below)) + rest0;
     } else {
-        const uint64_t o1_chunks = 1ull << (P.g1 - 3);
-        rest0 = (tile % o1_chunks) << 3;
+        const uint64_t o1_chunks = 1ull << (P.g1 - LOGE);
+        rest0 = (tile % o1_chunks) << LOGE;
         mid = tile / o1_chunks;
     }
 
-    fr x[8];
+    fr x[E];
     // ---- load (round-0 register layout: rows j * R/8 + q, column col)
     if (!P.last) {
         if (active) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < E; ++j) {
                 const uint32_t row = (uint32_t)j * rows8 + q;
                 const uint64_t a = in_base + ((uint64_t)row << P.below) + col;
                 x[j] = fe_load<FrParams>(P.src + a);
                 const uint64_t at = insert_bits(a, P.rk_pos, P.rk_bits, P.rk_val); // true coefficient index
-                if (P.pro_lo != nullptr && at < P.pro_size) {
+                if (P.pro_full != nullptr) {
+                    if (at < P.pro_size) x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.pro_full + at));
+                } else if (P.pro_lo != nullptr && at < P.pro_size) {
                     fr s = fe_mul(fe_load_nc<FrParams>(P.pro_hi + (at >> P.pro_split)),
                                   fe_load_nc<FrParams>(P.pro_lo + (at & ((1ull << P.pro_split) - 1))));
                     x[j] = fe_mul(x[j], s);
@@ -220,8 +285,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
         if (active) {
             const uint32_t mid_bits_total = P.mid_bits_total;
 #pragma unroll 1
-            for (uint32_t it = 0; it < 8; ++it) {
-                const uint32_t idx = it * R + tau;   // [0, 8R): column-major
+            for (uint32_t it = 0; it < (uint32_t)E; ++it) {
+                const uint32_t idx = it * R + tau;   // [0, E R): column-major
                 const uint32_t c = idx >> g, row = idx & (R - 1);
                 const uint64_t hi_idx = ((rest0 + c) << mid_bits_total) | mid;
                 uint64_t a;
@@ -239,16 +304,16 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
         __syncthreads();
         if (active) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < E; ++j) {
                 const uint32_t row = (uint32_t)j * rows8 + q;
                 x[j] = smem_load(sm, half_stride, sm_base + row * NTT_PAD + col);
             }
         }
     }
 
-    // ---- radix-8 rounds over row bits g-1 .. 0
+    // ---- radix-E rounds over row bits g-1 .. 0
     int b_hi = (int)g - 1;
-    uint32_t w0 = g - 3; // first round always has a full 3-bit window (g >= 3)
+    uint32_t w0 = g - LOGE; // first round always has a full LOGE-bit window (g >= LOGE)
     bool first = true;
     while (true) {
         if (!first) {
@@ -257,15 +322,15 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
             if (active) {
                 const uint32_t lo_part = q & ((1u << w0) - 1), hi_part = q >> w0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t row = (hi_part << (w0 + 3)) | ((uint32_t)j << w0) | lo_part;
+                for (int j = 0; j < E; ++j) {
+                    const uint32_t row = (hi_part << (w0 + LOGE)) | ((uint32_t)j << w0) | lo_part;
                     x[j] = smem_load(sm, half_stride, sm_base + row * NTT_PAD + col);
                 }
             }
         }
         const uint32_t lo_part = q & ((1u << w0) - 1);
         if (active) {
-            radix8_round(x, g, w0, (uint32_t)b_hi, lo_part, P.stage_tw);
+            radix_round<LOGE>(x, g, w0, (uint32_t)b_hi, lo_part, P.stage_tw);
         }
         b_hi = (int)w0 - 1;
         if (b_hi < 0) {
@@ -275,28 +340,33 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
         if (active) {
             const uint32_t hi_part = q >> w0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t row = (hi_part << (w0 + 3)) | ((uint32_t)j << w0) | lo_part;
+            for (int j = 0; j < E; ++j) {
+                const uint32_t row = (hi_part << (w0 + LOGE)) | ((uint32_t)j << w0) | lo_part;
                 smem_store(sm, half_stride, sm_base + row * NTT_PAD + col, x[j]);
             }
         }
         first = false;
-        w0 = b_hi >= 2 ? (uint32_t)b_hi - 2 : 0;
+        w0 = b_hi >= LOGE - 1 ? (uint32_t)b_hi - (LOGE - 1) : 0;
     }
 
-    // ---- store.  After the last round (w0 == 0) thread holds rows (q << 3) | j; row rho holds X[bitrev_g(rho)].
+    // ---- store.  After the last round (w0 == 0) thread holds rows (q << LOGE) | j; row rho holds X[bitrev_g(rho)].
     if (!active) {
         return;
     }
     if (!P.last) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t rho = (q << 3) | (uint32_t)j;
+        for (int j = 0; j < E; ++j) {
+            const uint32_t rho = (q << LOGE) | (uint32_t)j;
             const uint32_t o = bitrev(rho, g);
             const uint64_t rest = insert_bits(rest0 + col, P.rk_pos, P.rk_bits, P.rk_val);
             // inter-pass twiddle w_N^( 2^above * o * rest )
             uint64_t e = (((uint64_t)o * rest) << P.above) & (N - 1);
-            if (e != 0) {
+            if (P.tw_scaled != nullptr) {
+                if (P.inverse) {
+                    e = (N - e) & (N - 1);
+                }
+                x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.tw_scaled + e));
+            } else if (e != 0) {
                 if (P.inverse) {
                     e = N - e;
                 }
@@ -317,8 +387,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t rho = (q << 3) | (uint32_t)j;
+        for (int j = 0; j < E; ++j) {
+            const uint32_t rho = (q << LOGE) | (uint32_t)j;
             const uint64_t o = obase | ((uint64_t)bitrev(rho, g) << P.above);
             if (P.epi_mode == 1) {
                 x[j] = fe_mul(x[j], P.epi_const);
@@ -326,6 +396,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) k_ntt_pass(const PassParams P)
                 fr s = fe_mul(fe_load_nc<FrParams>(P.epi_hi + (o >> P.epi_split)),
                               fe_load_nc<FrParams>(P.epi_lo + (o & ((1ull << P.epi_split) - 1))));
                 x[j] = fe_mul(x[j], s);
+            } else if (P.epi_mode == 3) {
+                x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.epi_full + o));
             }
             const uint64_t ol = P.rk_bits ? squeeze_bits(o, P.g1, P.rk_bits) : o; // local slot of natural index o
             fe_store(P.dst + ((ol << P.out_shift) + P.out_off), x[j]);
@@ -471,6 +543,58 @@ static int ensure_big_table(Context* ctx, unsigned log_n, const fr** out, cudaSt
     return BBG_OK;
 }
 
+// Cached full table T[i] = start * shift^i, i < count (see Context::ntt_scale_cache).  *out stays nullptr when the key
+// is new (first sighting), too large, or the build failed; the caller then uses the two-level tables.
+static constexpr uint64_t NTT_SCALE_MAX_BYTES = 1ull << 30;  // per table
+static constexpr size_t NTT_SCALE_MAX_TABLES = 8;
+static int get_scale_table(Context* ctx, uint64_t count, const hf::Fr& start, const hf::Fr& shift, const fr** out, cudaStream_t st)
+{
+    *out = nullptr;
+    if (count == 0 || count * sizeof(fr) > NTT_SCALE_MAX_BYTES) return BBG_OK;
+    static const bool disabled = [] {
+        const char* v = getenv("BBG_NTT_NO_SCALE_CACHE");
+        return v && *v && atoi(v) != 0;
+    }();
+    if (disabled) return BBG_OK;
+    auto& cache = ctx->ntt_scale_cache;
+    const uint64_t now = ++ctx->ntt_scale_clock;
+    for (auto& e : cache) {
+        if (e.count == count && memcmp(e.start, start.d, 32) == 0 && memcmp(e.shift, shift.d, 32) == 0) {
+            e.last_use = now;
+            if (e.tab == nullptr) {
+                fr* tab = nullptr;
+                if (cudaMalloc(&tab, count * sizeof(fr)) != cudaSuccess) {
+                    cudaGetLastError(); // out of memory: keep using the two-level path
+                    return BBG_OK;
+                }
+                int rc = launch_powers(ctx, tab, count, shift, start, 0, st);
+                if (rc) {
+                    cudaFree(tab);
+                    return rc;
+                }
+                e.tab = tab;
+            }
+            *out = (const fr*)e.tab;
+            return BBG_OK;
+        }
+    }
+    if (cache.size() >= NTT_SCALE_MAX_TABLES) {
+        size_t victim = 0;
+        for (size_t i = 1; i < cache.size(); ++i) {
+            if (cache[i].last_use < cache[victim].last_use) victim = i;
+        }
+        if (cache[victim].tab) cudaFree(cache[victim].tab); // synchronises with any kernel still reading it
+        cache.erase(cache.begin() + (long)victim);
+    }
+    Context::ScaleTab e;
+    e.count = count;
+    memcpy(e.start, start.d, 32);
+    memcpy(e.shift, shift.d, 32);
+    e.last_use = now;
+    cache.push_back(e);
+    return BBG_OK;
+}
+
 // In-place (src == dst allowed) transform of 2^log_n elements on the device.
 //   pro : x[i] *= start * shift^i for i < size, before the transform
 //   epi : X[o] *= start (* shift^o), after the transform
@@ -541,7 +665,21 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
     const uint32_t split = (log_n + 1) / 2;
     const fr *pro_lo = nullptr, *pro_hi = nullptr, *epi_lo = nullptr, *epi_hi = nullptr;
     const uint64_t lo_count = 1ull << split, hi_count = 1ull << (log_n - split);
-    if (pro.present) {
+    const fr *pro_full = nullptr, *epi_full = nullptr, *tw_scaled = nullptr;
+    if (pro.present && rb == 0) {
+        if ((rc = get_scale_table(ctx, std::min<uint64_t>(pro.size, N), pro.start, pro.has_shift ? pro.shift : hf::one(), &pro_full, st))) return rc;
+    }
+    if (epi.present && epi.has_shift && rb == 0) {
+        if ((rc = get_scale_table(ctx, N, epi.start, epi.shift, &epi_full, st))) return rc;
+    }
+    if (epi.present && !epi.has_shift && rb == 0 && inverse) {
+        // plain ifft: fold 1/n into the last inter-pass twiddle (table 1/n * w^e, indexed by the forward exponent)
+        const hf::Fr n_inv = hf::invert(hf::from_u64(N));
+        if (memcmp(hf::reduce(epi.start).d, hf::reduce(n_inv).d, 32) == 0) {
+            if ((rc = get_scale_table(ctx, N, hf::reduce(n_inv), ntt_root_of_unity(log_n), &tw_scaled, st))) return rc;
+        }
+    }
+    if (pro.present && pro_full == nullptr) {
         if ((rc = ctx->ntt_pro.reserve((lo_count + hi_count) * sizeof(fr)))) return rc;
         fr* lo = (fr*)ctx->ntt_pro.p;
         fr* hi = lo + lo_count;
@@ -551,7 +689,7 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         pro_lo = lo;
         pro_hi = hi;
     }
-    if (epi.present && epi.has_shift) {
+    if (epi.present && epi.has_shift && epi_full == nullptr) {
         if ((rc = ctx->ntt_epi.reserve((lo_count + hi_count) * sizeof(fr)))) return rc;
         fr* lo = (fr*)ctx->ntt_epi.p;
         fr* hi = lo + lo_count;
@@ -563,9 +701,16 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
 
     static bool attr_set = false;
     if (!attr_set) {
-        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<3>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
         attr_set = true;
     }
+    // elements per thread (see NttGeom): 2^loge
+    static const unsigned loge_env = [] {
+        const char* v = getenv("BBG_NTT_LOGE");
+        return v && *v ? (unsigned)atoi(v) : NTT_DEFAULT_LOGE;
+    }();
+    const unsigned loge = loge_env == 2 ? 2 : 3;
 
     if (rb > 0 && (gb[num_passes - 1] < rb + 3 || gb[0] < rb + 3)) {
         set_last_error("ntt: too many ranks for this transform size");
@@ -627,6 +772,9 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         }
         pp.pro_lo = (p == 0) ? pro_lo : nullptr;
         pp.pro_hi = (p == 0) ? pro_hi : nullptr;
+        pp.pro_full = (p == 0) ? pro_full : nullptr;
+        pp.epi_full = nullptr;
+        pp.tw_scaled = (p + 2 == num_passes) ? tw_scaled : nullptr;
         pp.pro_split = split;
         pp.pro_size = pro.present ? pro.size : 0;
         pp.epi_mode = 0;
@@ -641,15 +789,25 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
                 pp.epi_lo = epi_lo;
                 pp.epi_hi = epi_hi;
                 pp.epi_const = to_dev(epi.start);
+                if (epi_full != nullptr) {
+                    pp.epi_mode = 3;
+                    pp.epi_full = epi_full;
+                } else if (tw_scaled != nullptr) {
+                    pp.epi_mode = 0; // the constant rode in on the previous pass's twiddles
+                }
             }
             pp.out_shift = out_shift;
             pp.out_off = out_off;
         }
-        const uint64_t num_tiles = (N >> rb) >> (gb[p] + 3);
+        const uint64_t num_tiles = (N >> rb) >> (gb[p] + loge);
         const unsigned tiles_per_cta = NTT_THREADS >> gb[p];
         const unsigned blocks = (unsigned)((num_tiles + tiles_per_cta - 1) / tiles_per_cta);
         pr.mark(st, PH_NTT_PASS0 + (int)p);
-        k_ntt_pass<<<blocks, NTT_THREADS, NTT_SMEM_BYTES, st>>>(pp);
+        if (loge == 2) {
+            k_ntt_pass<2><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
+        } else {
+            k_ntt_pass<3><<<blocks, NTT_THREADS, NttGeom<3>::SMEM_BYTES, st>>>(pp);
+        }
         ctx->launches += 1;
         above += gb[p];
     }

@@ -320,6 +320,7 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     gathered = torch.empty((world, 96), dtype=torch.uint8, device=dev)
     total = torch.empty(96, dtype=torch.uint8, device=dev)
+    sync_token = torch.zeros(1, dtype=torch.float32, device=dev)
 
     def msm_step():
         part = pip.pippenger_unsafe(sc_dev, 0, n)  # async on torch's current stream
@@ -343,6 +344,11 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     phase_ms = {}
     for k in range(K):
+        if world > 1:
+            # align the ranks before every timed step (outside the event pair, like the L2 flush): without it the
+            # host-side work between steps (flush launch, profile read-back) lets ranks drift, and the drift would be
+            # booked as all-gather time by whichever rank arrives first
+            dist.all_reduce(sync_token)
         ev[k][0].record()
         msm_step()
         ev[k][1].record()

@@ -286,6 +286,33 @@ def test_ntt_vs_oracle_all_sizes(bbg, orc, lg):
         assert np.array_equal(got, exp), (lg, kind)
 
 
+@pytest.mark.parametrize("lg", [6, 9, 12, 13, 17])
+def test_ntt_repeated_calls_use_cached_scale_tables(bbg, orc, lg):
+    """The library promotes a (constant, shift, size) scaling to a cached full table the SECOND time it sees it, and a
+    plain ifft then folds 1/n into its last inter-pass twiddles: results must not depend on which path ran.  Also cycles
+    through more distinct constants than the cache holds (eviction) and back."""
+    n = 1 << lg
+    x = inputs.fr_elements(900 + lg, n, coarse_fraction=0.25)
+    const = inputs.fr_elements(901 + lg, 1)[0]
+    exp = {}
+    for rep in range(3):
+        for kind in range(8):
+            for gs in ((0, n // 4) if kind in (2, 6, 7) else (0,)):
+                if (kind, gs) not in exp:
+                    exp[(kind, gs)] = canon(orc, orc.ntt(kind, x, generator_size=gs, constant=const))
+                got = canon(orc, bbg.ntt(x.copy(), kind, generator_size=gs, constant=const))
+                assert np.array_equal(got, exp[(kind, gs)]), (lg, kind, gs, rep)
+    if lg == 9:
+        consts = inputs.fr_elements(77, 12)
+        want = [canon(orc, orc.ntt(po.NTT_COSET_FFT_GEN_SHIFT, x, constant=c)) for c in consts]
+        for rep in range(3):
+            for c, w in zip(consts, want):
+                assert np.array_equal(canon(orc, bbg.coset_fft_with_generator_shift(x.copy(), c)), w), rep
+        # and the first keys again, after they were evicted
+        got = canon(orc, bbg.ntt(x.copy(), bbg.COSET_IFFT))
+        assert np.array_equal(got, exp[(bbg.COSET_IFFT, 0)])
+
+
 def test_ntt_device_pointer_entry(bbg, orc):
     import torch
     n = 1 << 12
