@@ -42,7 +42,7 @@ template <int LOGE> struct NttGeom {
     static constexpr int PAD = E + 1;                           // row pitch in 16-byte units (E columns + 1 pad)
     static constexpr int HALF_STRIDE = NTT_THREADS * PAD;       // 16-byte units between the two halves of an element
     static constexpr int SMEM_BYTES = 2 * HALF_STRIDE * 16;     // E = 8: 73,728 B; E = 4: 40,960 B
-    static constexpr int MIN_CTAS = LOGE == 3 ? 2 : 3;
+    static constexpr int MIN_CTAS = LOGE == 3 ? 2 : (LOGE == 2 ? 3 : 4);
 };
 static constexpr int NTT_MAX_PASSES = 4;
 static constexpr unsigned NTT_DEFAULT_LOGE = 2; // measured at 2^22: fft 0.892 ms with E = 4 vs 0.948 ms with E = 8 (BBG_NTT_LOGE=3)
@@ -703,14 +703,17 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
     if (!attr_set) {
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<3>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<1>::SMEM_BYTES));
         attr_set = true;
     }
-    // elements per thread (see NttGeom): 2^loge
+    // elements per thread (see NttGeom): 2^loge.  Measured on B200 (fft, ms; E = 2 / 4 / 8): 2^16 0.039 / 0.052 / 0.102 (the grid is
+    // only n / (256 E) CTAs there), 2^18 0.091 / 0.088 / 0.116, 2^20 0.249 / 0.241 / 0.287, 2^22 0.948 / 0.892 / 0.948,
+    // 2^24 3.94 / 3.55 / 3.75.
     static const unsigned loge_env = [] {
         const char* v = getenv("BBG_NTT_LOGE");
-        return v && *v ? (unsigned)atoi(v) : NTT_DEFAULT_LOGE;
+        return v && *v ? (unsigned)atoi(v) : 0u;
     }();
-    const unsigned loge = loge_env == 2 ? 2 : 3;
+    const unsigned loge = (loge_env >= 1 && loge_env <= 3) ? loge_env : (log_n <= 16 ? 1u : NTT_DEFAULT_LOGE);
 
     if (rb > 0 && (gb[num_passes - 1] < rb + 3 || gb[0] < rb + 3)) {
         set_last_error("ntt: too many ranks for this transform size");
@@ -803,7 +806,9 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         const unsigned tiles_per_cta = NTT_THREADS >> gb[p];
         const unsigned blocks = (unsigned)((num_tiles + tiles_per_cta - 1) / tiles_per_cta);
         pr.mark(st, PH_NTT_PASS0 + (int)p);
-        if (loge == 2) {
+        if (loge == 1) {
+            k_ntt_pass<1><<<blocks, NTT_THREADS, NttGeom<1>::SMEM_BYTES, st>>>(pp);
+        } else if (loge == 2) {
             k_ntt_pass<2><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
         } else {
             k_ntt_pass<3><<<blocks, NTT_THREADS, NttGeom<3>::SMEM_BYTES, st>>>(pp);
