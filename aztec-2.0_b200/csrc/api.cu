@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" boundary of libbbg.so (declared in include/bbg.h).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -10,6 +11,7 @@
 #include "ctx.cuh"
 #include "g1.cuh"
 #include "internal.hpp"
+#include "staging.hpp"
 
 namespace bbg {
 
@@ -69,13 +71,22 @@ int get_context(Context** out)
     return BBG_OK;
 }
 
-// RAII device timer around the kernels of one host-pointer call
+static Staging g_staging; // pinned staging buffers + copy threads for pageable host memory (staging.hpp)
+
+// RAII device timer around the kernels of one host-pointer call: construct after the H2D copies are queued, stop()
+// before the D2H copies are queued, finish() after them (synchronises the stream).
 struct DeviceTimer {
     Context* c;
+    bool stopped = false;
     explicit DeviceTimer(Context* ctx) : c(ctx) { cudaEventRecord(c->ev_a, c->stream); }
+    void stop()
+    {
+        cudaEventRecord(c->ev_b, c->stream);
+        stopped = true;
+    }
     int finish()
     {
-        BBG_CUDA(cudaEventRecord(c->ev_b, c->stream));
+        if (!stopped) stop();
         BBG_CUDA(cudaStreamSynchronize(c->stream));
         float ms = 0.f;
         BBG_CUDA(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
@@ -83,6 +94,66 @@ struct DeviceTimer {
         return BBG_OK;
     }
 };
+
+// ---- BBG_STATS=1: wall time / device time / PCIe bytes spent inside the host-pointer entry points, printed to stderr at
+// exit.  Lets a drop-in user see how much of (say) a proof is the hot path and how much of THAT is pageable copies.
+struct HostStats {
+    struct Row {
+        const char* name;
+        uint64_t calls = 0, bytes_h2d = 0, bytes_d2h = 0;
+        double wall_s = 0, device_ms = 0;
+    };
+    Row rows[3] = { { "msm" }, { "ntt" }, { "srs" } };
+    bool enabled = false;
+    bool per_call = false; // BBG_STATS=2: one stderr line per call as well
+    HostStats()
+    {
+        const char* v = getenv("BBG_STATS");
+        enabled = v && *v && atoi(v) != 0;
+        per_call = enabled && atoi(v) >= 2;
+    }
+    ~HostStats()
+    {
+        if (!enabled) return;
+        for (const Row& r : rows) {
+            if (r.calls == 0) continue;
+            fprintf(stderr, "{\"bbg_stats\": \"%s\", \"calls\": %llu, \"wall_s\": %.6f, \"device_kernel_s\": %.6f, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu}\n",
+                    r.name, (unsigned long long)r.calls, r.wall_s, r.device_ms * 1e-3, (unsigned long long)r.bytes_h2d,
+                    (unsigned long long)r.bytes_d2h);
+        }
+    }
+};
+static HostStats g_stats;
+struct StatScope {
+    HostStats::Row* row;
+    Context* ctx;
+    std::chrono::steady_clock::time_point t0;
+    uint64_t h2d, d2h, launches0 = 0;
+    StatScope(int which, Context* c, uint64_t h2d_, uint64_t d2h_)
+        : row(g_stats.enabled ? &g_stats.rows[which] : nullptr), ctx(c), h2d(h2d_), d2h(d2h_)
+    {
+        if (!row) return;
+        launches0 = ctx->launches;
+        t0 = std::chrono::steady_clock::now();
+        row->calls += 1;
+        row->bytes_h2d += h2d;
+        row->bytes_d2h += d2h;
+        ctx->last_kernel_ms = 0.0;
+    }
+    ~StatScope()
+    {
+        if (!row) return;
+        const double w = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        row->wall_s += w;
+        row->device_ms += ctx->last_kernel_ms;
+        if (g_stats.per_call) {
+            fprintf(stderr, "{\"bbg_call\": \"%s\", \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"wall_ms\": %.3f, \"device_kernel_ms\": %.3f, \"kernels\": %llu}\n",
+                    row->name, (unsigned long long)h2d, (unsigned long long)d2h, w * 1e3, ctx->last_kernel_ms,
+                    (unsigned long long)(ctx->launches - launches0));
+        }
+    }
+};
+enum { STAT_MSM = 0, STAT_NTT = 1, STAT_SRS = 2 };
 
 // ---- Pippenger object: the SRS resident in HBM as n contiguous affine points
 struct PippengerObj {
@@ -390,6 +461,9 @@ void bbg_shutdown(void)
     }
     g_pippengers.clear();
     for (auto& kv : g_ctx->ntt_twiddles) cudaFree(kv.second);
+    for (auto& e : g_ctx->ntt_scale_cache) {
+        if (e.tab) cudaFree(e.tab);
+    }
     for (int d = 0; d < 2; ++d) {
         if (g_ctx->ntt_stage_tw[d]) cudaFree(g_ctx->ntt_stage_tw[d]);
     }
@@ -397,6 +471,7 @@ void bbg_shutdown(void)
                        &g_ctx->msm_buckets, &g_ctx->msm_partials, &g_ctx->msm_reduce, &g_ctx->msm_scan_tmp, &g_ctx->msm_result,
                        &g_ctx->msm_points, &g_ctx->msm_lvl_offsets, &g_ctx->msm_pairs_a, &g_ctx->msm_pairs_b, &g_ctx->msm_pair_pre, &g_ctx->msm_pair_meta, &g_ctx->msm_pts0, &g_ctx->ntt_data, &g_ctx->ntt_scratch, &g_ctx->ntt_pro, &g_ctx->ntt_epi, &g_ctx->ntt_small };
     for (auto* b : bufs) b->release();
+    g_staging.release();
     cudaEventDestroy(g_ctx->ev_a);
     cudaEventDestroy(g_ctx->ev_b);
     cudaStreamDestroy(g_ctx->stream);
@@ -595,11 +670,13 @@ static int msm_host_scalars(Context* ctx, const void* scalars, size_t n, const a
                             size_t base, void* result)
 {
     int rc;
+    StatScope stat(STAT_MSM, ctx, n * 32, 96);
     if ((rc = ctx->msm_scalars.reserve(std::max<size_t>(n, 1) * 32))) return rc;
     if ((rc = ctx->msm_result.reserve(96))) return rc;
-    if (n) BBG_CUDA(cudaMemcpyAsync(ctx->msm_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (n && (rc = g_staging.h2d(ctx->msm_scalars.p, scalars, n * 32, ctx->stream))) return rc;
     DeviceTimer tm(ctx);
     if ((rc = msm_device(ctx, ctx->msm_scalars.p, n, d_points, stride, lv, base, ctx->msm_result.p, ctx->stream))) return rc;
+    tm.stop();
     BBG_CUDA(cudaMemcpyAsync(result, ctx->msm_result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
     return tm.finish();
 }
@@ -787,11 +864,13 @@ int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void*
     bool inverse;
     NttScale pro, epi;
     if ((rc = ntt_kind_params(kind, lg, generator_size, constant, inverse, pro, epi))) return rc;
+    StatScope stat(STAT_NTT, ctx, n * 32, n * 32);
     if ((rc = ctx->ntt_data.reserve(n * 32))) return rc;
-    BBG_CUDA(cudaMemcpyAsync(ctx->ntt_data.p, coeffs, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = g_staging.h2d(ctx->ntt_data.p, coeffs, n * 32, ctx->stream))) return rc;
     DeviceTimer tm(ctx);
     if ((rc = ntt_device(ctx, ctx->ntt_data.p, ctx->ntt_data.p, lg, inverse, pro, epi, 0, 0, ctx->stream))) return rc;
-    BBG_CUDA(cudaMemcpyAsync(coeffs, ctx->ntt_data.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    tm.stop();
+    if ((rc = g_staging.d2h(coeffs, ctx->ntt_data.p, n * 32, ctx->stream))) return rc;
     return tm.finish();
 }
 
@@ -893,11 +972,13 @@ int bbg_coset_fft_ext(void* coeffs, size_t n, size_t domain_extension)
     unsigned lg;
     int rc = log2_exact(n, lg);
     if (rc) return rc;
+    StatScope stat(STAT_NTT, ctx, n * 32, n * domain_extension * 32);
     if ((rc = ctx->ntt_data.reserve(n * domain_extension * 32))) return rc;
-    BBG_CUDA(cudaMemcpyAsync(ctx->ntt_data.p, coeffs, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = g_staging.h2d(ctx->ntt_data.p, coeffs, n * 32, ctx->stream))) return rc;
     DeviceTimer tm(ctx);
     if ((rc = coset_fft_ext_device(ctx, ctx->ntt_data.p, lg, domain_extension, ctx->stream))) return rc;
-    BBG_CUDA(cudaMemcpyAsync(coeffs, ctx->ntt_data.p, n * domain_extension * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    tm.stop();
+    if ((rc = g_staging.d2h(coeffs, ctx->ntt_data.p, n * domain_extension * 32, ctx->stream))) return rc;
     return tm.finish();
 }
 
