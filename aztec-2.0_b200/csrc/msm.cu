@@ -1237,7 +1237,8 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     // chunking: equal work per thread; about two waves of resident threads, chunk >= 16 entries.
     // The number of non-zero digits is only known on the device; size for the maximum.
     const size_t resident = (size_t)ctx->num_sms * ACC_THREADS * 4;
-    size_t chunk = (acc_entries + 2 * resident - 1) / (2 * resident);
+    const size_t waves = std::max(1u, env_uint("BBG_MSM_WAVES", 2));
+    size_t chunk = (acc_entries + waves * resident - 1) / (waves * resident);
     if (chunk < 16) chunk = 16;
     const size_t num_chunks = (acc_entries + chunk - 1) / chunk;
     // slot arrays of all merge levels, back to back

@@ -384,6 +384,8 @@ def coset_fft_with_generator_shift(c, value, generator_size=0, **kw):
 def coset_fft_ext(coeffs, n, domain_extension, stream=None):
     """coset_fft(coeffs, small_domain, large_domain, ext): coeffs holds ext*n elements, first n = input."""
     if isinstance(coeffs, np.ndarray):
+        assert coeffs.dtype == np.uint64 and coeffs.flags["C_CONTIGUOUS"] and coeffs.size >= 4 * n * domain_extension, \
+            "coset_fft_ext writes ext*n elements into coeffs"
         _check(lib.bbg_coset_fft_ext(coeffs.ctypes.data, n, domain_extension))
     else:
         _check(lib.bbg_coset_fft_ext_dev(coeffs.data_ptr(), n, domain_extension, _stream_ptr(stream)))

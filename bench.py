@@ -168,9 +168,20 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
 def cpu_checker():
+    """The CPU arm: the compiled reference when it travelled (all host threads), else the scalar plain-C port.
+    torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm must still use the whole host, so the
+    thread count is set explicitly: the largest power of two <= the cores this process may run on (SURVEY.md 8d;
+    barretenberg's own thread split assumes a power of two, bb/common/max_threads.hpp)."""
     from oracle import pyoracle as po
     if po.Ref.available():
-        return po.Ref(), "reference"
+        ref = po.Ref()
+        try:
+            avail = len(os.sched_getaffinity(0))
+        except Exception:
+            avail = os.cpu_count() or 1
+        want = int(os.environ.get("BBG_CPU_THREADS", "0")) or (1 << (max(1, avail).bit_length() - 1))
+        ref.set_num_threads(want)
+        return ref, "reference"
     return po.Oracle(), "port"
 
 
