@@ -192,6 +192,37 @@ template <class F> __device__ __forceinline__ Fe<F> fe_sub(const Fe<F>& a, const
     add8_masked_2p<F>(r.l, d.l, borrow);
     return r;
 }
+// a - b + 2p with NO reduction: for a, b in [0, 2p) the result lies in (0, 4p) < 2^256.  Only legal as the left operand of
+// a Montgomery multiply whose other operand is canonical (< p): (4p * p) / 2^256 + p < 1.76 p, back inside [0, 2p).
+// Saves the borrow extraction and the eight masking instructions of fe_sub (used by the NTT butterflies, whose
+// twiddle tables are stored canonical).
+template <class F> __device__ __forceinline__ Fe<F> fe_sub_lazy(const Fe<F>& a, const Fe<F>& b)
+{
+    Fe<F> d, r;
+    asm("sub.cc.u32 %0, %8, %16;\n\t"
+        "subc.cc.u32 %1, %9, %17;\n\t"
+        "subc.cc.u32 %2, %10, %18;\n\t"
+        "subc.cc.u32 %3, %11, %19;\n\t"
+        "subc.cc.u32 %4, %12, %20;\n\t"
+        "subc.cc.u32 %5, %13, %21;\n\t"
+        "subc.cc.u32 %6, %14, %22;\n\t"
+        "subc.u32 %7, %15, %23;"
+        : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]), "=r"(d.l[6]), "=r"(d.l[7])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+        : "r"(d.l[0]), "r"(d.l[1]), "r"(d.l[2]), "r"(d.l[3]), "r"(d.l[4]), "r"(d.l[5]), "r"(d.l[6]), "r"(d.l[7]),
+          "n"(F::P2(0)), "n"(F::P2(1)), "n"(F::P2(2)), "n"(F::P2(3)), "n"(F::P2(4)), "n"(F::P2(5)), "n"(F::P2(6)), "n"(F::P2(7)));
+    return r;
+}
 template <class F> __device__ __forceinline__ Fe<F> fe_dbl(const Fe<F>& a) { return fe_add(a, a); }
 // -a = 2p - a (field_impl.hpp:148-157); maps 0 -> 2p which is still a legal coarse zero? No: 2p is out of
 // range, so zero is mapped to zero explicitly.

@@ -118,7 +118,7 @@ __device__ __forceinline__ fr smem_load(const uint4* sm, uint32_t half_stride, u
 __device__ __forceinline__ void bfly(fr& u, fr& v, const fr& w)
 {
     fr s = fe_add(u, v);
-    fr d = fe_sub(u, v);
+    fr d = fe_sub_lazy(u, v); // (0, 4p): legal because w comes from a canonical table (k_powers stores reduce_once'd values)
     u = s;
     v = fe_mul(d, w);
 }

@@ -528,6 +528,12 @@ def bench_ntt(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq_muls, b
         barrier()
         per[name] = {"ms": max_over_ranks(ms) / K}
         per[name]["elements_per_s"] = world * n / (per[name]["ms"] * 1e-3)
+    ntt_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ntt_traffic = json.load(f).get("k_ntt_pass_2^%d" % lg)
+    except Exception:
+        ntt_traffic = None
     bbg.profile(False)
     launches = bbg.kernel_launches() - launches0
     # e2e: host buffer in place through bbg_ntt (H2D + D2H of 32 n bytes each inside the call)
@@ -549,7 +555,7 @@ def bench_ntt(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq_muls, b
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_ntt_pass", "achieved": (64.0 * n / (kern_ms * 1e-3) / 1e9) if kern_ms else None,
                      "peak": hbm_gbs, "unit": "GB/s", "frac": (64.0 * n / (kern_ms * 1e-3) / 1e9 / hbm_gbs) if kern_ms else None,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": 64.0 * n, "kernel_ms": kern_ms,
+                     "traffic": ntt_traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": 64.0 * n, "kernel_ms": kern_ms,
                      "transform_frac": 64.0 * n / (mean_ms * 1e-3) / 1e9 / hbm_gbs,
                      "note": "each pass reads and writes the array once (64 n B); a transform is %d passes; the passes are integer-pipe bound" % passes},
         "int_pipe": {"unit": "G fr-mul/s", "peak": fq_muls / 1e9, "achieved": muls / (mean_ms * 1e-3) / 1e9,
