@@ -52,6 +52,8 @@ static int create_context(int device)
     c->num_sms = prop.multiProcessorCount;
     if (getenv("BBG_STACK")) BBG_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(getenv("BBG_STACK"))));
     BBG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    BBG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev_piece) BBG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     BBG_CUDA(cudaEventCreate(&c->ev_a));
     BBG_CUDA(cudaEventCreate(&c->ev_b));
     g_ctx = c;
@@ -475,6 +477,8 @@ void bbg_shutdown(void)
     cudaEventDestroy(g_ctx->ev_a);
     cudaEventDestroy(g_ctx->ev_b);
     cudaStreamDestroy(g_ctx->stream);
+    cudaStreamDestroy(g_ctx->copy_stream);
+    for (auto& e : g_ctx->ev_piece) cudaEventDestroy(e);
     delete g_ctx;
     g_ctx = nullptr;
 }
@@ -673,9 +677,33 @@ static int msm_host_scalars(Context* ctx, const void* scalars, size_t n, const a
     StatScope stat(STAT_MSM, ctx, n * 32, 96);
     if ((rc = ctx->msm_scalars.reserve(std::max<size_t>(n, 1) * 32))) return rc;
     if ((rc = ctx->msm_result.reserve(96))) return rc;
-    if (n && (rc = g_staging.h2d(ctx->msm_scalars.p, scalars, n * 32, ctx->stream))) return rc;
+    // Large pinned scalar arrays go up in pieces on the copy stream; the histogram pass of msm_device chases them piece by
+    // piece (it is the only phase that can start before every scalar is on the device).
+    MsmArrival arrival;
+    const size_t pieces = 4;
+    const bool piecewise = n >= (1u << 18) && !Staging::pageable(scalars);
+    if (piecewise) {
+        // order the copies after whatever last used msm_scalars on the work stream
+        BBG_CUDA(cudaEventRecord(ctx->ev_piece[pieces], ctx->stream));
+        BBG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_piece[pieces], 0));
+        arrival.ready = ctx->ev_piece;
+        arrival.count = pieces;
+        arrival.piece = ((n + pieces - 1) / pieces + 255) & ~(size_t)255;
+        for (size_t k = 0; k < pieces; ++k) {
+            const size_t lo = k * arrival.piece;
+            const size_t len = lo < n ? std::min(arrival.piece, n - lo) : 0;
+            if (len) {
+                BBG_CUDA(cudaMemcpyAsync((char*)ctx->msm_scalars.p + lo * 32, (const char*)scalars + lo * 32, len * 32,
+                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+            BBG_CUDA(cudaEventRecord(ctx->ev_piece[k], ctx->copy_stream));
+        }
+    } else if (n && (rc = g_staging.h2d(ctx->msm_scalars.p, scalars, n * 32, ctx->stream))) {
+        return rc;
+    }
     DeviceTimer tm(ctx);
-    if ((rc = msm_device(ctx, ctx->msm_scalars.p, n, d_points, stride, lv, base, ctx->msm_result.p, ctx->stream))) return rc;
+    if ((rc = msm_device(ctx, ctx->msm_scalars.p, n, d_points, stride, lv, base, ctx->msm_result.p, ctx->stream,
+                         piecewise ? &arrival : nullptr))) return rc;
     tm.stop();
     BBG_CUDA(cudaMemcpyAsync(result, ctx->msm_result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
     return tm.finish();

@@ -81,6 +81,8 @@ struct Context {
     int device = -1;
     int num_sms = 148;
     cudaStream_t stream = nullptr; // default work stream for the host-pointer entry points
+    cudaStream_t copy_stream = nullptr; // H2D pieces that overlap with kernels on `stream`
+    cudaEvent_t ev_piece[8] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // MSM workspaces
     DevBuf msm_scalars, msm_counts, msm_offsets, msm_cursors, msm_sorted, msm_buckets, msm_partials, msm_reduce,

@@ -15,8 +15,15 @@ struct MsmLevels {
 };
 MsmLevels msm_levels_plan(size_t n, size_t max_table_bytes);
 int msm_precompute_device(Context* ctx, void* d_table, size_t n, const MsmLevels& lv, cudaStream_t st);
+// Scalars still in flight from the host: `count` equal pieces of `piece` scalars each (the last may be short); piece k is
+// valid on the device once ready[k] has fired.  msm_device then runs the histogram pass piece by piece behind the copies.
+struct MsmArrival {
+    const cudaEvent_t* ready = nullptr;
+    size_t count = 0;
+    size_t piece = 0;
+};
 int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_points, size_t point_stride, const MsmLevels& lv,
-               size_t base, void* d_out, cudaStream_t st);
+               size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival = nullptr);
 int g1_sum_device(Context* ctx, const void* d_jacs, size_t n, void* d_out, cudaStream_t st);
 int srs_decode_device(Context* ctx, const void* d_raw, size_t n, void* d_points, cudaStream_t st);
 int point_table_device(Context* ctx, const void* d_points, size_t n, void* d_table, cudaStream_t st);

@@ -1102,7 +1102,7 @@ int msm_precompute_device(Context* ctx, void* d_table, size_t n, const MsmLevels
 // Device-pointer MSM over table entries [base, base + n) of level 0 (and the same range of every other level).
 //   lv.L == 1: plain points (any stride), W bucket sets.   lv.L > 1: fixed-base levels, S = D / c bucket sets.
 int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_points, size_t point_stride, const MsmLevels& lv_in,
-               size_t base, void* d_out, cudaStream_t st)
+               size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival)
 {
     Profiler& pr = ctx->prof;
     pr.begin();
@@ -1163,8 +1163,22 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     }
     dp.agg_from = env_uint("BBG_MSM_AGG_FROM", dp.agg_from);
     const unsigned dig_blocks = div_up(n, 256);
-    k_msm_digits<DIG_HISTOGRAM><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, counts, nullptr, nullptr, 0, nullptr);
-    ctx->launches += 1;
+    if (arrival != nullptr && arrival->count > 1) {
+        // the histogram does not care which scalar a digit came from: count every piece as soon as its copy has landed
+        for (size_t k = 0; k < arrival->count; ++k) {
+            const size_t lo = k * arrival->piece;
+            if (lo >= n) break;
+            DigitParams dk = dp;
+            dk.n = (uint32_t)std::min(arrival->piece, n - lo);
+            BBG_CUDA(cudaStreamWaitEvent(st, arrival->ready[k], 0));
+            k_msm_digits<DIG_HISTOGRAM><<<div_up(dk.n, 256), 256, 0, st>>>((const fr_t*)d_scalars + lo, dk, counts, nullptr, nullptr, 0, nullptr);
+            ctx->launches += 1;
+        }
+    } else {
+        if (arrival != nullptr && arrival->count == 1) BBG_CUDA(cudaStreamWaitEvent(st, arrival->ready[0], 0));
+        k_msm_digits<DIG_HISTOGRAM><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, counts, nullptr, nullptr, 0, nullptr);
+        ctx->launches += 1;
+    }
     pr.mark(st, PH_MSM_SCAN);
     if ((rc = exclusive_scan(ctx, counts, G, offsets, cursors, st))) return rc;
     // ---- optional pairwise affine passes (k_msm_pair_pass): J levels, each halving every bucket's entry count.

@@ -110,6 +110,20 @@ def test_msm_2p20_linearity_and_ranges(bbg, orc, full_srs):
     assert orc.jac_to_buffer(bbg.g1_sum(np.stack(parts))) == orc.jac_to_buffer(ra)
 
 
+def test_msm_pinned_scalars_piecewise_upload(bbg, orc, full_srs):
+    """Pinned host scalars take the piecewise upload (copy stream + histogram chasing the pieces, api.cu
+    msm_host_scalars); pageable ones the plain path.  Same bytes in, same point out -- also for ragged sizes whose last
+    piece is short or empty."""
+    for seed, n in ((31, FULL), (32, FULL - 1000), (33, (1 << 18) + 1), (34, (3 << 18) + 77)):
+        sc = inputs.fr_elements(seed, n, coarse_fraction=0.01)
+        pinned = bbg.pinned_empty((n, 4))
+        pinned[...] = sc
+        a = orc.jac_to_buffer(full_srs.pippenger_unsafe(sc, 0, n))
+        b = orc.jac_to_buffer(full_srs.pippenger_unsafe(pinned, 0, n))
+        assert a == b, (seed, n)
+        bbg.pinned_free(pinned)
+
+
 def test_msm_2p20_structured_scalars(bbg, orc, full_srs):
     """All-equal scalars put every window's digits in ONE bucket per window (worst-case skew at full size):
     msm(k, ..., k) == k * msm(1, ..., 1)."""
