@@ -138,6 +138,44 @@ def test_msm_2p20_structured_scalars(bbg, orc, full_srs):
     assert orc.jac_to_buffer(sk) == orc.jac_to_buffer(exp)
 
 
+def test_msm_2p24_linearity_and_sharding_synthetic_points(bbg, orc):
+    """North-star sizes beyond the shipped SRS (2^22 ... 2^26): bases are the SRS followed by distinct synthetic points
+    P_i + D_k built on the device (never replicate points), exactly as bench.py does.  No CPU checker runs
+    at this size in seconds, so the evidence is structural: linearity in the scalars, and the reference's own
+    from/range + g1_sum sharding (what the multi-GPU path does) against the single MSM."""
+    import torch
+    if not os.path.exists(os.path.join(po.REF_SRS_DIR, "transcript00.dat")):
+        pytest.skip("full SRS did not travel")
+    lg = 24
+    n = 1 << lg
+    srs = bbg.read_transcript_g1(FULL, po.REF_SRS_DIR)
+    dev = torch.device("cuda", 0)
+    srs_dev = torch.from_numpy(srs.view(np.int64)).to(dev)
+    pts = torch.empty((n, 8), dtype=torch.int64, device=dev)
+    for blk in range(n // FULL):
+        if blk == 0:
+            pts[:FULL] = srs_dev
+        else:
+            bbg.g1_add_affine(srs_dev, srs[blk], out_dev=pts[blk * FULL:(blk + 1) * FULL])
+    torch.cuda.synchronize()
+    pip = bbg.Pippenger.from_device_points(pts, n)
+    del pts, srs_dev
+    a = inputs.fr_elements(61, n)
+    b = inputs.fr_elements(62, n)
+    ra = pip.pippenger_unsafe(a, 0, n)
+    rb = pip.pippenger_unsafe(b, 0, n)
+    rab = pip.pippenger_unsafe(np_fr_add(a, b), 0, n)
+    assert orc.jac_to_buffer(bbg.g1_sum(np.stack([ra, rb]))) == orc.jac_to_buffer(rab)
+    cuts = [0, n // 8, n // 2 + 3, n - (1 << 20) - 1, n]
+    parts = [pip.pippenger_unsafe(a[lo:hi], lo, hi - lo) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    assert orc.jac_to_buffer(bbg.g1_sum(np.stack(parts))) == orc.jac_to_buffer(ra)
+    # the first 2^20 bases are the real SRS: that range must agree with the SRS-only object's result
+    base = bbg.Pippenger.from_path(po.REF_SRS_DIR, FULL)
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(a[:FULL], 0, FULL)) == orc.jac_to_buffer(base.pippenger_unsafe(a[:FULL], 0, FULL))
+    pip.close()
+    base.close()
+
+
 @pytest.mark.parametrize("lg", [20, 22])
 def test_ntt_fullsize_matches_reference_cpu(bbg, orc, lg):
     """config #3: fr radix-2 NTT / iNTT / coset_fft at 2^22 vs the reference's CPU polynomial_arithmetic."""
