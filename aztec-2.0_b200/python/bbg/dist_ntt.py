@@ -26,18 +26,21 @@ def insert_shard(out, shard, pos, world, rank):
     out.reshape(n // (low * world), world, low, 4)[:, rank] = shard.reshape(n // (low * world), low, 4)
 
 
-def ntt_sharded(bbg, local_in, n, kind, rank, world, generator_size=0, constant=None, group=None):
-    """local_in: torch CUDA int64 tensor (n / world, 4) = this rank's input shard.  Returns this rank's output shard."""
+def ntt_sharded(bbg, local_in, n, kind, rank, world, generator_size=0, constant=None, group=None, phase_fn=None):
+    """local_in: torch int64 tensor (n / world, 4) = this rank's input shard (CUDA in the product).  Returns this rank's
+    output shard.  phase_fn(src, dst, n, kind, rank, world, phase, generator_size, constant) defaults to libbbg's
+    bbg_ntt_dist_dev; tests/test_sharded_cpu.py injects a CPU stand-in to run this plumbing under gloo."""
     import torch
     import torch.distributed as dist
+    phase = bbg.ntt_dist_phase if phase_fn is None else phase_fn
     mid = torch.empty_like(local_in)
-    bbg.ntt_dist_phase(local_in, mid, n, kind, rank, world, 0, generator_size, constant)
+    phase(local_in, mid, n, kind, rank, world, 0, generator_size, constant)
     if world == 1:
         return mid
     recv = torch.empty_like(mid)
     dist.all_to_all_single(recv, mid, group=group)  # chunk r of every rank -> rank r, in source-rank order
     out = torch.empty_like(mid)
-    bbg.ntt_dist_phase(recv, out, n, kind, rank, world, 1, generator_size, constant)
+    phase(recv, out, n, kind, rank, world, 1, generator_size, constant)
     return out
 
 
