@@ -58,11 +58,11 @@ def peaks():
 def srs_dir_and_capacity():
     """The reference's shipped 2^20-point transcript travels in oracle/_ref/srs_db (git-ignored); the committed
     4096-point excerpt is the fallback."""
-    from oracle import pyoracle as po
     import inputs
-    full = os.path.join(po.REF_SRS_DIR, "transcript00.dat")
+    ref_srs_dir = os.path.join(ROOT, "oracle", "_ref", "srs_db")  # a DATA file of the reference; no oracle code is imported here
+    full = os.path.join(ref_srs_dir, "transcript00.dat")
     if os.path.exists(full):
-        return po.REF_SRS_DIR, 1 << 20
+        return ref_srs_dir, 1 << 20
     return inputs.SRS_MINI_DIR, inputs.SRS_MINI_POINTS
 
 
@@ -277,8 +277,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import bbg
-    import inputs
-    from oracle import pyoracle as po
+    import inputs  # tests/inputs.py: seeded numpy generators only (the oracle is NOT imported by this arm)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
