@@ -78,3 +78,34 @@ def test_compute_entry_points_fail_loudly_without_a_device(lib):
     assert not out.any(), "no result may be written by a failed call"
     lib.bbg_new_pippenger_from_points.restype = ctypes.c_void_p
     assert not lib.bbg_new_pippenger_from_points(ctypes.c_void_p(pts.ctypes.data), ctypes.c_size_t(4))
+
+
+def test_host_side_domain_constants_and_layout_need_no_device():
+    """Pure host code of the library (csrc/host_field.hpp): evaluation_domain constants (root, root^-1, n, n^-1, g, g^-1;
+    bb/polynomials/evaluation_domain.cpp:57-76) against the oracle for every power of two up to fr's 2-adicity, the golden
+    vectors, and the multi-GPU NTT layout contract."""
+    sys.path.insert(0, os.path.join(ROOT, "aztec-2.0_b200", "python"))
+    sys.path.insert(0, ROOT)
+    import json
+    import bbg
+    from oracle import pyoracle as po
+    orc = po.Oracle()
+    for lg in range(1, 29):
+        a = bbg.domain_constants(1 << lg)
+        b = orc.domain_constants(1 << lg)
+        assert np.array_equal(orc.reduce(po.FR, a), orc.reduce(po.FR, b)), lg
+    with pytest.raises(bbg.BbgError):
+        bbg.domain_constants(3)
+    with open(os.path.join(ROOT, "tests", "golden", "vectors.json")) as f:
+        golden = json.load(f)
+    for lg in (12, 16, 20, 22, 24, 25, 26, 28):
+        for world in (2, 4, 8):
+            in_pos, out_pos = bbg.ntt_dist_layout(1 << lg, world)
+            passes = 2 if lg <= 16 else (3 if lg <= 24 else 4)
+            first = lg // passes + (1 if lg % passes else 0)
+            last = lg // passes + (1 if (passes - 1) < lg % passes else 0)
+            rb = world.bit_length() - 1
+            assert (in_pos, out_pos) == (last - rb, first - rb), (lg, world)
+    with pytest.raises(bbg.BbgError):
+        bbg.ntt_dist_layout(1 << 12, 3)
+    assert "fields" in golden  # the fixture the GPU parity tests read is present in the tree
