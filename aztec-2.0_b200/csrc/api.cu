@@ -7,11 +7,7 @@
 #include <memory>
 #include <string>
 
-#include "../../include/bbg.h"
-#include "ctx.cuh"
-#include "g1.cuh"
-#include "internal.hpp"
-#include "staging.hpp"
+#include "api_common.hpp"
 
 namespace bbg {
 
@@ -53,13 +49,19 @@ static int create_context(int device)
     if (getenv("BBG_STACK")) BBG_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(getenv("BBG_STACK"))));
     BBG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     BBG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    BBG_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     for (auto& e : c->ev_piece) BBG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     BBG_CUDA(cudaEventCreate(&c->ev_a));
     BBG_CUDA(cudaEventCreate(&c->ev_b));
+    BBG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    BBG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    BBG_CUDA(cudaEventCreateWithFlags(&c->last_use, cudaEventDisableTiming));
     g_ctx = c;
     return BBG_OK;
 }
 
+// Callers may come from any thread and may have another device current (a PyTorch process): every entry point binds the
+// context's device for its own duration and puts the caller's device back on exit (DeviceGuard inside GET_CTX).
 int get_context(Context** out)
 {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -67,104 +69,27 @@ int get_context(Context** out)
         int rc = create_context(-1);
         if (rc) return rc;
     }
-    // callers may come from any thread: bind the device for this thread
-    BBG_CUDA(cudaSetDevice(g_ctx->device));
     *out = g_ctx;
     return BBG_OK;
 }
+DeviceGuard::DeviceGuard(int device)
+{
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) {
+        cudaSetDevice(device);
+    } else {
+        prev = -1; // nothing to restore
+    }
+}
+DeviceGuard::~DeviceGuard()
+{
+    if (prev >= 0) cudaSetDevice(prev);
+}
 
-static Staging g_staging; // pinned staging buffers + copy threads for pageable host memory (staging.hpp)
+Staging g_staging;
+HostStats g_stats;
+std::vector<PippengerObj*> g_pippengers;
 
-// RAII device timer around the kernels of one host-pointer call: construct after the H2D copies are queued, stop()
-// before the D2H copies are queued, finish() after them (synchronises the stream).
-struct DeviceTimer {
-    Context* c;
-    bool stopped = false;
-    explicit DeviceTimer(Context* ctx) : c(ctx) { cudaEventRecord(c->ev_a, c->stream); }
-    void stop()
-    {
-        cudaEventRecord(c->ev_b, c->stream);
-        stopped = true;
-    }
-    int finish()
-    {
-        if (!stopped) stop();
-        BBG_CUDA(cudaStreamSynchronize(c->stream));
-        float ms = 0.f;
-        BBG_CUDA(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
-        c->last_kernel_ms = ms;
-        return BBG_OK;
-    }
-};
-
-// ---- BBG_STATS=1: wall time / device time / PCIe bytes spent inside the host-pointer entry points, printed to stderr at
-// exit.  Lets a drop-in user see how much of (say) a proof is the hot path and how much of THAT is pageable copies.
-struct HostStats {
-    struct Row {
-        const char* name;
-        uint64_t calls = 0, bytes_h2d = 0, bytes_d2h = 0;
-        double wall_s = 0, device_ms = 0;
-    };
-    Row rows[3] = { { "msm" }, { "ntt" }, { "srs" } };
-    bool enabled = false;
-    bool per_call = false; // BBG_STATS=2: one stderr line per call as well
-    HostStats()
-    {
-        const char* v = getenv("BBG_STATS");
-        enabled = v && *v && atoi(v) != 0;
-        per_call = enabled && atoi(v) >= 2;
-    }
-    ~HostStats()
-    {
-        if (!enabled) return;
-        for (const Row& r : rows) {
-            if (r.calls == 0) continue;
-            fprintf(stderr, "{\"bbg_stats\": \"%s\", \"calls\": %llu, \"wall_s\": %.6f, \"device_kernel_s\": %.6f, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu}\n",
-                    r.name, (unsigned long long)r.calls, r.wall_s, r.device_ms * 1e-3, (unsigned long long)r.bytes_h2d,
-                    (unsigned long long)r.bytes_d2h);
-        }
-    }
-};
-static HostStats g_stats;
-struct StatScope {
-    HostStats::Row* row;
-    Context* ctx;
-    std::chrono::steady_clock::time_point t0;
-    uint64_t h2d, d2h, launches0 = 0;
-    StatScope(int which, Context* c, uint64_t h2d_, uint64_t d2h_)
-        : row(g_stats.enabled ? &g_stats.rows[which] : nullptr), ctx(c), h2d(h2d_), d2h(d2h_)
-    {
-        if (!row) return;
-        launches0 = ctx->launches;
-        t0 = std::chrono::steady_clock::now();
-        row->calls += 1;
-        row->bytes_h2d += h2d;
-        row->bytes_d2h += d2h;
-        ctx->last_kernel_ms = 0.0;
-    }
-    ~StatScope()
-    {
-        if (!row) return;
-        const double w = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        row->wall_s += w;
-        row->device_ms += ctx->last_kernel_ms;
-        if (g_stats.per_call) {
-            fprintf(stderr, "{\"bbg_call\": \"%s\", \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"wall_ms\": %.3f, \"device_kernel_ms\": %.3f, \"kernels\": %llu}\n",
-                    row->name, (unsigned long long)h2d, (unsigned long long)d2h, w * 1e3, ctx->last_kernel_ms,
-                    (unsigned long long)(ctx->launches - launches0));
-        }
-    }
-};
-enum { STAT_MSM = 0, STAT_NTT = 1, STAT_SRS = 2 };
-
-// ---- Pippenger object: the SRS resident in HBM as n contiguous affine points
-struct PippengerObj {
-    affine_t* d_points = nullptr;     // level 0 = the n SRS points; levels 1..L-1 follow (msm.cu k_msm_precompute)
-    size_t n = 0;
-    MsmLevels lv;
-    const void* host_table = nullptr; // adopted 2n host table (for pointer recognition), may be null
-};
-static std::vector<PippengerObj*> g_pippengers;
 static int g_auto_adopt = -1; // -1: read BBG_AUTO_ADOPT on first use
 
 static int upload_even_entries(Context* ctx, const void* table2n, size_t n, affine_t* d_points)
@@ -309,6 +234,20 @@ __global__ void k_g1_op(int op, const jac_t* a, const void* b, jac_t* out, size_
     fe_store(&out[i].z, r.z);
 }
 
+// g1::affine_element(element) (bb/ecc/groups/element_impl.hpp:51-68): Jacobian -> canonical affine, one inversion each
+__global__ void __launch_bounds__(64) k_g1_normalize(const jac_t* __restrict__ in, affine_t* __restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    jac_t j;
+    j.x = fe_load<FqParams>(&in[i].x);
+    j.y = fe_load<FqParams>(&in[i].y);
+    j.z = fe_load<FqParams>(&in[i].z);
+    affine_t r = xyzz_to_affine(xyzz_from_jacobian(j));
+    fe_store(&out[i].x, r.x);
+    fe_store(&out[i].y, r.y);
+}
+
 template <class F> __global__ void __launch_bounds__(256) k_bench_mul(Fe<F>* out, int iters)
 {
     Fe<F> x, y;
@@ -432,13 +371,6 @@ struct DomainObj {
 
 using namespace bbg;
 
-#define GET_CTX()                     \
-    Context* ctx = nullptr;           \
-    {                                 \
-        int _rc = get_context(&ctx);  \
-        if (_rc) return _rc;          \
-    }                                 \
-    std::lock_guard<std::mutex> _lk(ctx->mu)
 
 extern "C" {
 
@@ -446,6 +378,11 @@ int bbg_init(int device)
 {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     if (g_ctx != nullptr) {
+        if (device >= 0 && device != g_ctx->device) {
+            set_last_error("bbg_init: the library is already bound to device " + std::to_string(g_ctx->device) +
+                           " (an earlier call created the context); call bbg_shutdown() first");
+            return BBG_ERR_ARG;
+        }
         return BBG_OK;
     }
     return create_context(device);
@@ -457,11 +394,15 @@ void bbg_shutdown(void)
     if (g_ctx == nullptr) return;
     cudaSetDevice(g_ctx->device);
     cudaDeviceSynchronize();
+    // Handles stay valid as *names* only: the objects are freed here, and bbg_delete_pippenger / any later use of a stale
+    // handle finds it absent from g_pippengers and does nothing (Python's Pippenger.__del__ at interpreter exit, the
+    // shim's ~Pippenger during static destruction).
     for (auto* o : g_pippengers) {
         cudaFree(o->d_points);
         delete o;
     }
     g_pippengers.clear();
+    resident_clear(g_ctx);
     for (auto& kv : g_ctx->ntt_twiddles) cudaFree(kv.second);
     for (auto& e : g_ctx->ntt_scale_cache) {
         if (e.tab) cudaFree(e.tab);
@@ -469,15 +410,25 @@ void bbg_shutdown(void)
     for (int d = 0; d < 2; ++d) {
         if (g_ctx->ntt_stage_tw[d]) cudaFree(g_ctx->ntt_stage_tw[d]);
     }
-    DevBuf* bufs[] = { &g_ctx->msm_scalars, &g_ctx->msm_counts, &g_ctx->msm_offsets, &g_ctx->msm_cursors, &g_ctx->msm_sorted,
-                       &g_ctx->msm_buckets, &g_ctx->msm_partials, &g_ctx->msm_reduce, &g_ctx->msm_scan_tmp, &g_ctx->msm_result,
-                       &g_ctx->msm_points, &g_ctx->msm_lvl_offsets, &g_ctx->msm_pairs_a, &g_ctx->msm_pairs_b, &g_ctx->msm_pair_pre, &g_ctx->msm_pair_meta, &g_ctx->msm_pts0, &g_ctx->ntt_data, &g_ctx->ntt_scratch, &g_ctx->ntt_pro, &g_ctx->ntt_epi, &g_ctx->ntt_small };
+    g_ctx->ntt_twiddles.clear();
+    g_ctx->ntt_scale_cache.clear();
+    for (auto& ws : g_ctx->msm_ws) ws.release();
+    DevBuf* bufs[] = { &g_ctx->msm_points, &g_ctx->ntt_data, &g_ctx->ntt_scratch, &g_ctx->ntt_pro, &g_ctx->ntt_epi, &g_ctx->ntt_small,
+                       &g_ctx->poly_tmp };
     for (auto* b : bufs) b->release();
+    if (g_ctx->inv_fix_fq) cudaFree(g_ctx->inv_fix_fq);
+    for (auto& e : g_ctx->prof.ev) {
+        if (e) cudaEventDestroy(e);
+    }
     g_staging.release();
     cudaEventDestroy(g_ctx->ev_a);
     cudaEventDestroy(g_ctx->ev_b);
+    cudaEventDestroy(g_ctx->ev_fork);
+    cudaEventDestroy(g_ctx->ev_join);
+    cudaEventDestroy(g_ctx->last_use);
     cudaStreamDestroy(g_ctx->stream);
     cudaStreamDestroy(g_ctx->copy_stream);
+    cudaStreamDestroy(g_ctx->aux_stream);
     for (auto& e : g_ctx->ev_piece) cudaEventDestroy(e);
     delete g_ctx;
     g_ctx = nullptr;
@@ -494,6 +445,7 @@ int bbg_device_count(void)
 uint64_t bbg_kernel_launches(void) { return g_ctx ? g_ctx->launches : 0; }
 double bbg_last_device_ms(void) { return g_ctx ? g_ctx->last_kernel_ms : 0.0; }
 
+static_assert(BBG_NUM_PHASES == PH_COUNT, "include/bbg.h BBG_NUM_PHASES must cover every Phase");
 int bbg_profile(int enable)
 {
     GET_CTX();
@@ -520,6 +472,7 @@ void* bbg_malloc(size_t size)
 {
     Context* ctx = nullptr;
     if (get_context(&ctx)) return nullptr;
+    DeviceGuard dg(ctx->device);
     void* p = nullptr;
     if (cudaHostAlloc(&p, size ? size : 1, cudaHostAllocDefault) != cudaSuccess) {
         set_last_error("cudaHostAlloc failed");
@@ -541,7 +494,11 @@ static void* finish_obj(Context* ctx, PippengerObj* o, int rc)
         rc = BBG_ERR_CUDA;
     }
     if (rc != BBG_OK) {
-        bbg_delete_pippenger(o);
+        // ctx->mu is held by the caller: drop the object here instead of going through bbg_delete_pippenger
+        auto it = std::find(g_pippengers.begin(), g_pippengers.end(), o);
+        if (it != g_pippengers.end()) g_pippengers.erase(it);
+        if (o->d_points) cudaFree(o->d_points);
+        delete o;
         return nullptr;
     }
     return o;
@@ -549,9 +506,8 @@ static void* finish_obj(Context* ctx, PippengerObj* o, int rc)
 
 void* bbg_new_pippenger(const uint8_t* points, size_t num_points)
 {
-    Context* ctx = nullptr;
-    if (get_context(&ctx)) return nullptr;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    GET_CTX_PTR();
+    StreamScope order(ctx, ctx->stream);
     PippengerObj* o = new_obj(ctx, num_points);
     if (!o) return nullptr;
     int rc = BBG_OK;
@@ -564,8 +520,10 @@ void* bbg_new_pippenger(const uint8_t* points, size_t num_points)
 
 void* bbg_new_pippenger_from_path(const char* srs_dir, size_t num_points)
 {
-    Context* ctx = nullptr;
-    if (get_context(&ctx)) return nullptr;
+    {
+        Context* ctx = nullptr;
+        if (get_context(&ctx)) return nullptr;
+    }
     std::vector<uint8_t> raw;
     if (read_transcript_raw(srs_dir, num_points, raw)) return nullptr;
     return bbg_new_pippenger(raw.data(), num_points);
@@ -573,9 +531,8 @@ void* bbg_new_pippenger_from_path(const char* srs_dir, size_t num_points)
 
 void* bbg_new_pippenger_from_table(const void* table2n, size_t num_points)
 {
-    Context* ctx = nullptr;
-    if (get_context(&ctx)) return nullptr;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    GET_CTX_PTR();
+    StreamScope order(ctx, ctx->stream);
     PippengerObj* o = new_obj(ctx, num_points);
     if (!o) return nullptr;
     o->host_table = table2n;
@@ -585,9 +542,8 @@ void* bbg_new_pippenger_from_table(const void* table2n, size_t num_points)
 
 void* bbg_new_pippenger_from_points(const void* points, size_t num_points)
 {
-    Context* ctx = nullptr;
-    if (get_context(&ctx)) return nullptr;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    GET_CTX_PTR();
+    StreamScope order(ctx, ctx->stream);
     PippengerObj* o = new_obj(ctx, num_points);
     if (!o) return nullptr;
     int rc = BBG_OK;
@@ -600,9 +556,8 @@ void* bbg_new_pippenger_from_points(const void* points, size_t num_points)
 
 void* bbg_new_pippenger_from_device_points(const void* d_points, size_t num_points)
 {
-    Context* ctx = nullptr;
-    if (get_context(&ctx)) return nullptr;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    GET_CTX_PTR();
+    StreamScope order(ctx, ctx->stream);
     PippengerObj* o = new_obj(ctx, num_points);
     if (!o) return nullptr;
     int rc = BBG_OK;
@@ -627,6 +582,7 @@ int bbg_pippenger_bind_host_table(void* pippenger, const void* table2n)
 
 int bbg_set_auto_adopt(int enable)
 {
+    GET_CTX();
     g_auto_adopt = enable ? 1 : 0;
     return BBG_OK;
 }
@@ -635,8 +591,13 @@ void bbg_delete_pippenger(void* pippenger)
 {
     PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
     if (!o) return;
+    std::lock_guard<std::mutex> glk(g_ctx_mu);
+    if (g_ctx == nullptr) return; // after bbg_shutdown every handle is already gone
+    std::lock_guard<std::mutex> lk(g_ctx->mu);
     auto it = std::find(g_pippengers.begin(), g_pippengers.end(), o);
-    if (it != g_pippengers.end()) g_pippengers.erase(it);
+    if (it == g_pippengers.end()) return; // stale handle (freed by bbg_shutdown or deleted twice): never dereferenced
+    g_pippengers.erase(it);
+    DeviceGuard dg(g_ctx->device);
     if (o->d_points) cudaFree(o->d_points);
     delete o;
 }
@@ -649,6 +610,7 @@ unsigned bbg_pippenger_levels(void* pippenger) { return pippenger ? reinterpret_
 int bbg_pippenger_get_point_table(void* pippenger, void* table2n_out)
 {
     GET_CTX();
+    StreamScope order(ctx, ctx->stream);
     PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
     if (!o || !table2n_out) {
         set_last_error("null argument");
@@ -674,16 +636,29 @@ static int msm_host_scalars(Context* ctx, const void* scalars, size_t n, const a
                             size_t base, void* result)
 {
     int rc;
-    StatScope stat(STAT_MSM, ctx, n * 32, 96);
-    if ((rc = ctx->msm_scalars.reserve(std::max<size_t>(n, 1) * 32))) return rc;
-    if ((rc = ctx->msm_result.reserve(96))) return rc;
+    MsmWorkspace& ws = ctx->msm_ws[0];
+    StreamScope order(ctx, ctx->stream);
+    if ((rc = ws.result.reserve(96))) return rc;
+    // resident mirror of the scalar array (an ifft result, a slice of the quotient polynomial)?
+    void* d_res = nullptr;
+    bool hit = false;
+    if (n && (rc = resident_acquire(ctx, scalars, n * 32, true, &d_res, &hit, ctx->stream))) return rc;
+    StatScope stat(STAT_MSM, ctx, hit ? 0 : n * 32, 96);
+    if (d_res != nullptr) {
+        DeviceTimer tm(ctx);
+        if ((rc = msm_device(ctx, ws, d_res, n, d_points, stride, lv, base, ws.result.p, ctx->stream))) return rc;
+        tm.stop();
+        BBG_CUDA(cudaMemcpyAsync(result, ws.result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+        return tm.finish();
+    }
+    if ((rc = ws.scalars.reserve(std::max<size_t>(n, 1) * 32))) return rc;
     // Large pinned scalar arrays go up in pieces on the copy stream; the histogram pass of msm_device chases them piece by
     // piece (it is the only phase that can start before every scalar is on the device).
     MsmArrival arrival;
     const size_t pieces = 4;
     const bool piecewise = n >= (1u << 18) && !Staging::pageable(scalars);
     if (piecewise) {
-        // order the copies after whatever last used msm_scalars on the work stream
+        // order the copies after whatever last used the scalar buffer on the work stream
         BBG_CUDA(cudaEventRecord(ctx->ev_piece[pieces], ctx->stream));
         BBG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_piece[pieces], 0));
         arrival.ready = ctx->ev_piece;
@@ -693,19 +668,19 @@ static int msm_host_scalars(Context* ctx, const void* scalars, size_t n, const a
             const size_t lo = k * arrival.piece;
             const size_t len = lo < n ? std::min(arrival.piece, n - lo) : 0;
             if (len) {
-                BBG_CUDA(cudaMemcpyAsync((char*)ctx->msm_scalars.p + lo * 32, (const char*)scalars + lo * 32, len * 32,
+                BBG_CUDA(cudaMemcpyAsync((char*)ws.scalars.p + lo * 32, (const char*)scalars + lo * 32, len * 32,
                                          cudaMemcpyHostToDevice, ctx->copy_stream));
             }
             BBG_CUDA(cudaEventRecord(ctx->ev_piece[k], ctx->copy_stream));
         }
-    } else if (n && (rc = g_staging.h2d(ctx->msm_scalars.p, scalars, n * 32, ctx->stream))) {
+    } else if (n && (rc = g_staging.h2d(ws.scalars.p, scalars, n * 32, ctx->stream))) {
         return rc;
     }
     DeviceTimer tm(ctx);
-    if ((rc = msm_device(ctx, ctx->msm_scalars.p, n, d_points, stride, lv, base, ctx->msm_result.p, ctx->stream,
+    if ((rc = msm_device(ctx, ws, ws.scalars.p, n, d_points, stride, lv, base, ws.result.p, ctx->stream,
                          piecewise ? &arrival : nullptr))) return rc;
     tm.stop();
-    BBG_CUDA(cudaMemcpyAsync(result, ctx->msm_result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    BBG_CUDA(cudaMemcpyAsync(result, ws.result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
     return tm.finish();
 }
 
@@ -736,7 +711,127 @@ int bbg_pippenger_unsafe_dev(void* pippenger, const void* d_scalars, size_t from
         set_last_error("pippenger_unsafe: [from, from+range) exceeds the SRS");
         return BBG_ERR_SRS;
     }
-    return msm_device(ctx, d_scalars, range, o->d_points, 1, o->lv, from, d_result, (cudaStream_t)stream);
+    StreamScope order(ctx, (cudaStream_t)stream);
+    return msm_device(ctx, ctx->msm_ws[0], d_scalars, range, o->d_points, 1, o->lv, from, d_result, (cudaStream_t)stream);
+}
+
+// Several MSMs over the same bases in one call (the prover commits to its four wire polynomials, then to the four
+// slices of the quotient polynomial, back to back: prover.cpp:66-82, 84-135).  MSM i runs on stream i & 1 with workspace
+// i & 1, so the latency-bound tail of one MSM (slot merge, bucket reduction: a few hundred lone warps) overlaps the
+// throughput-bound bucket accumulation of the next.
+static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, bool device_scalars, size_t count, size_t from,
+                     size_t range, void* results, bool device_results, cudaStream_t st0)
+{
+    int rc;
+    StreamScope order(ctx, st0);
+    cudaStream_t st[2] = { st0, ctx->aux_stream };
+    if (count > 1) {
+        BBG_CUDA(cudaEventRecord(ctx->ev_fork, st0));
+        BBG_CUDA(cudaStreamWaitEvent(st[1], ctx->ev_fork, 0));
+    }
+    uint64_t h2d = 0;
+    StatScope stat(STAT_MSM, ctx, 0, device_results ? 0 : 96 * count);
+    for (size_t i = 0; i < count; ++i) {
+        MsmWorkspace& ws = ctx->msm_ws[i & 1];
+        cudaStream_t s = st[i & 1];
+        const void* d_sc = scalars[i];
+        if (!device_scalars) {
+            void* d_res = nullptr;
+            bool hit = false;
+            if (range && (rc = resident_acquire(ctx, scalars[i], range * 32, true, &d_res, &hit, s))) return rc;
+            if (d_res != nullptr) {
+                d_sc = d_res;
+                if (!hit) h2d += range * 32;
+            } else {
+                if ((rc = ws.scalars.reserve(std::max<size_t>(range, 1) * 32))) return rc;
+                if (range && (rc = g_staging.h2d(ws.scalars.p, scalars[i], range * 32, s))) return rc;
+                d_sc = ws.scalars.p;
+                h2d += range * 32;
+            }
+        }
+        void* d_out = device_results ? (char*)results + i * 96 : nullptr;
+        if (!device_results) {
+            if ((rc = ws.result.reserve(96))) return rc;
+            d_out = ws.result.p;
+        }
+        if ((rc = msm_device(ctx, ws, d_sc, range, o->d_points, 1, o->lv, from, d_out, s))) return rc;
+        if (!device_results) BBG_CUDA(cudaMemcpyAsync((char*)results + i * 96, d_out, 96, cudaMemcpyDeviceToHost, s));
+    }
+    if (stat.row) stat.row->bytes_h2d += h2d;
+    stat.h2d = h2d;
+    if (count > 1) {
+        BBG_CUDA(cudaEventRecord(ctx->ev_join, st[1]));
+        BBG_CUDA(cudaStreamWaitEvent(st0, ctx->ev_join, 0));
+    }
+    if (!device_results) BBG_CUDA(cudaStreamSynchronize(st0));
+    return BBG_OK;
+}
+
+int bbg_pippenger_unsafe_batch(void* pippenger, const void* const* scalars, size_t count, size_t from, size_t range, void* results)
+{
+    GET_CTX();
+    PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
+    if (!o || (count && (!scalars || !results))) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    if (from + range > o->n) {
+        set_last_error("pippenger_unsafe_batch: [from, from+range) exceeds the SRS");
+        return BBG_ERR_SRS;
+    }
+    return msm_batch(ctx, o, scalars, false, count, from, range, results, false, ctx->stream);
+}
+
+int bbg_pippenger_unsafe_batch_dev(void* pippenger, const void* const* d_scalars, size_t count, size_t from, size_t range,
+                                   void* d_results, void* stream)
+{
+    GET_CTX();
+    PippengerObj* o = reinterpret_cast<PippengerObj*>(pippenger);
+    if (!o || (count && (!d_scalars || !d_results))) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    if (from + range > o->n) {
+        set_last_error("pippenger_unsafe_batch: [from, from+range) exceeds the SRS");
+        return BBG_ERR_SRS;
+    }
+    return msm_batch(ctx, o, d_scalars, true, count, from, range, d_results, true, (cudaStream_t)stream);
+}
+
+// the Pippenger object whose adopted host table contains `points_table2n` (ProverReferenceString::get_monomials() or
+// monomials + 2 * from); *from receives the offset in points
+static PippengerObj* find_adopted(const void* points_table2n, size_t num_points, size_t* from)
+{
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(points_table2n);
+    for (auto* o : g_pippengers) {
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(o->host_table);
+        if (base && p >= base && p < base + o->n * 128 && (size_t)(p - base) % 128 == 0) {
+            const size_t f = (size_t)(p - base) / 128;
+            if (f + num_points <= o->n) {
+                *from = f;
+                return o;
+            }
+        }
+    }
+    return nullptr;
+}
+
+// batch flavour of bbg_pippenger(): `count` scalar arrays over the SAME interleaved table, which must belong to an
+// adopted Pippenger object (bbg_pippenger_bind_host_table / bbg_new_pippenger_from_table); BBG_ERR_ARG otherwise.
+int bbg_pippenger_batch(const void* const* scalars, size_t count, const void* points_table2n, size_t num_points, void* results)
+{
+    GET_CTX();
+    if (count && (!scalars || !results || !points_table2n)) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    size_t from = 0;
+    PippengerObj* o = find_adopted(points_table2n, num_points, &from);
+    if (o == nullptr) {
+        set_last_error("pippenger_batch: the point table is not resident (adopt it with bbg_pippenger_bind_host_table)");
+        return BBG_ERR_ARG;
+    }
+    return msm_batch(ctx, o, scalars, false, count, from, num_points, results, false, ctx->stream);
 }
 
 int bbg_pippenger(const void* scalars, const void* points_table2n, size_t num_points, int handle_edge_cases, void* result)
@@ -748,14 +843,10 @@ int bbg_pippenger(const void* scalars, const void* points_table2n, size_t num_po
         return BBG_ERR_ARG;
     }
     // resident copy?  (points may be monomials + 2*from, bb/.../pippenger.cpp:27-31)
-    const uint8_t* p = reinterpret_cast<const uint8_t*>(points_table2n);
-    for (auto* o : g_pippengers) {
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(o->host_table);
-        if (base && p >= base && p < base + o->n * 128 && (size_t)(p - base) % 128 == 0) {
-            size_t from = (size_t)(p - base) / 128;
-            if (from + num_points <= o->n) {
-                return msm_host_scalars(ctx, scalars, num_points, o->d_points, 1, o->lv, from, result);
-            }
+    {
+        size_t from = 0;
+        if (PippengerObj* o = find_adopted(points_table2n, num_points, &from)) {
+            return msm_host_scalars(ctx, scalars, num_points, o->d_points, 1, o->lv, from, result);
         }
     }
     int rc;
@@ -793,12 +884,15 @@ int bbg_msm_points(const void* scalars, const void* points, size_t num_points, v
 int bbg_msm_points_dev(const void* d_scalars, const void* d_points, size_t point_stride, size_t num_points, void* d_result, void* stream)
 {
     GET_CTX();
-    return msm_device(ctx, d_scalars, num_points, d_points, point_stride ? point_stride : 1, MsmLevels(), 0, d_result, (cudaStream_t)stream);
+    StreamScope order(ctx, (cudaStream_t)stream);
+    return msm_device(ctx, ctx->msm_ws[0], d_scalars, num_points, d_points, point_stride ? point_stride : 1, MsmLevels(), 0, d_result,
+                      (cudaStream_t)stream);
 }
 
 int bbg_generate_pippenger_point_table(const void* points, void* table, size_t num_points)
 {
     GET_CTX();
+    StreamScope order(ctx, ctx->stream);
     if (num_points == 0) return BBG_OK;
     void *d_pts = nullptr, *d_table = nullptr;
     BBG_CUDA(cudaMalloc(&d_pts, num_points * 64));
@@ -826,23 +920,27 @@ int bbg_g1_sum(const void* elements, size_t num_points, void* result)
 {
     GET_CTX();
     int rc;
+    MsmWorkspace& ws = ctx->msm_ws[0];
+    StreamScope order(ctx, ctx->stream);
     if ((rc = ctx->msm_points.reserve(std::max<size_t>(num_points, 1) * 96))) return rc;
-    if ((rc = ctx->msm_result.reserve(96))) return rc;
+    if ((rc = ws.result.reserve(96))) return rc;
     if (num_points) BBG_CUDA(cudaMemcpyAsync(ctx->msm_points.p, elements, num_points * 96, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = g1_sum_device(ctx, ctx->msm_points.p, num_points, ctx->msm_result.p, ctx->stream))) return rc;
-    BBG_CUDA(cudaMemcpyAsync(result, ctx->msm_result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = g1_sum_device(ctx, ctx->msm_points.p, num_points, ws.result.p, ctx->stream))) return rc;
+    BBG_CUDA(cudaMemcpyAsync(result, ws.result.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
     BBG_CUDA(cudaStreamSynchronize(ctx->stream));
     return BBG_OK;
 }
 int bbg_g1_sum_dev(const void* d_elements, size_t num_points, void* d_result, void* stream)
 {
     GET_CTX();
+    StreamScope order(ctx, (cudaStream_t)stream);
     return g1_sum_device(ctx, d_elements, num_points, d_result, (cudaStream_t)stream);
 }
 
 int bbg_read_g1_elements_from_buffer(void* elements, const char* buffer, size_t buffer_size)
 {
     GET_CTX();
+    StreamScope order(ctx, ctx->stream);
     size_t n = buffer_size / 64;
     if (n == 0) return BBG_OK;
     void* d_out = nullptr;
@@ -874,6 +972,7 @@ int bbg_read_transcript_g1(void* monomials, size_t degree, const char* srs_dir)
 int bbg_ntt_dev(void* d_coeffs, size_t n, int kind, size_t generator_size, const void* constant, void* stream)
 {
     GET_CTX();
+    StreamScope order(ctx, (cudaStream_t)stream);
     unsigned lg;
     int rc = log2_exact(n, lg);
     if (rc) return rc;
@@ -886,13 +985,25 @@ int bbg_ntt_dev(void* d_coeffs, size_t n, int kind, size_t generator_size, const
 int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant)
 {
     GET_CTX();
+    StreamScope order(ctx, ctx->stream);
     unsigned lg;
     int rc = log2_exact(n, lg);
     if (rc) return rc;
     bool inverse;
     NttScale pro, epi;
     if ((rc = ntt_kind_params(kind, lg, generator_size, constant, inverse, pro, epi))) return rc;
-    StatScope stat(STAT_NTT, ctx, n * 32, n * 32);
+    void* d_res = nullptr;
+    bool hit = false;
+    if ((rc = resident_acquire(ctx, coeffs, n * 32, true, &d_res, &hit, ctx->stream))) return rc;
+    StatScope stat(STAT_NTT, ctx, hit ? 0 : n * 32, n * 32);
+    if (d_res != nullptr) {
+        // resident mirror: transform it in place and bring the result home; the mirror stays valid for the next call
+        DeviceTimer tm(ctx);
+        if ((rc = ntt_device(ctx, d_res, d_res, lg, inverse, pro, epi, 0, 0, ctx->stream))) return rc;
+        tm.stop();
+        if ((rc = resident_commit(ctx, coeffs, n * 32, true, ctx->stream))) return rc;
+        return tm.finish();
+    }
     if ((rc = ctx->ntt_data.reserve(n * 32))) return rc;
     if ((rc = g_staging.h2d(ctx->ntt_data.p, coeffs, n * 32, ctx->stream))) return rc;
     DeviceTimer tm(ctx);
@@ -931,6 +1042,7 @@ int bbg_ntt_dist_dev(const void* d_src, void* d_dst, size_t n, int kind, size_t 
                      int world, int phase, void* stream)
 {
     GET_CTX();
+    StreamScope order(ctx, (cudaStream_t)stream);
     unsigned lg;
     int rc = log2_exact(n, lg);
     if (rc) return rc;
@@ -988,6 +1100,7 @@ static int coset_fft_ext_device(Context* ctx, void* d_coeffs, unsigned lg, size_
 int bbg_coset_fft_ext_dev(void* d_coeffs, size_t n, size_t domain_extension, void* stream)
 {
     GET_CTX();
+    StreamScope order(ctx, (cudaStream_t)stream);
     unsigned lg;
     int rc = log2_exact(n, lg);
     if (rc) return rc;
@@ -997,6 +1110,7 @@ int bbg_coset_fft_ext_dev(void* d_coeffs, size_t n, size_t domain_extension, voi
 int bbg_coset_fft_ext(void* coeffs, size_t n, size_t domain_extension)
 {
     GET_CTX();
+    StreamScope order(ctx, ctx->stream);
     unsigned lg;
     int rc = log2_exact(n, lg);
     if (rc) return rc;
@@ -1043,6 +1157,7 @@ int bbg_domain_constants(size_t n, void* out6)
 int bbg_bench_field_mul(int field, int iters, double* muls_per_second)
 {
     GET_CTX();
+    StreamScope order(ctx, ctx->stream);
     if (!muls_per_second || iters <= 0) {
         set_last_error("bad argument");
         return BBG_ERR_ARG;
@@ -1078,6 +1193,7 @@ int bbg_bench_field_mul(int field, int iters, double* muls_per_second)
 int bbg_g1_add_affine_dev(const void* d_in, void* d_out, size_t n, const void* q_affine, void* stream)
 {
     GET_CTX();
+    StreamScope order(ctx, (cudaStream_t)stream);
     if (n == 0) return BBG_OK;
     affine_t q;
     memcpy(&q, q_affine, 64);
@@ -1091,6 +1207,7 @@ int bbg_g1_add_affine_dev(const void* d_in, void* d_out, size_t n, const void* q
 int bbg_field_op(int field, int op, const void* a, const void* b, void* out, size_t n)
 {
     GET_CTX();
+    StreamScope order(ctx, ctx->stream);
     if (n == 0) return BBG_OK;
     void *da = nullptr, *db = nullptr, *dout = nullptr;
     BBG_CUDA(cudaMalloc(&da, n * 32));
@@ -1112,9 +1229,53 @@ int bbg_field_op(int field, int op, const void* a, const void* b, void* out, siz
     return BBG_OK;
 }
 
+int bbg_field_op_dev(int field, int op, const void* d_a, const void* d_b, void* d_out, size_t n, void* stream)
+{
+    GET_CTX();
+    StreamScope order(ctx, (cudaStream_t)stream);
+    if (n == 0) return BBG_OK;
+    if (field == 0) {
+        k_field_op<FqParams><<<div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(op, (const fq_t*)d_a, (const fq_t*)d_b, (fq_t*)d_out, n);
+    } else {
+        k_field_op<FrParams><<<div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(op, (const fr_t*)d_a, (const fr_t*)d_b, (fr_t*)d_out, n);
+    }
+    ctx->launches += 1;
+    BBG_CUDA(cudaGetLastError());
+    return BBG_OK;
+}
+
+int bbg_g1_normalize(const void* elements, size_t n, void* affine_out)
+{
+    GET_CTX();
+    StreamScope order(ctx, ctx->stream);
+    if (n == 0) return BBG_OK;
+    void *d_in = nullptr, *d_out = nullptr;
+    BBG_CUDA(cudaMalloc(&d_in, n * 96));
+    if (cudaMalloc(&d_out, n * 64) != cudaSuccess) {
+        cudaFree(d_in);
+        set_last_error("cudaMalloc failed");
+        return BBG_ERR_CUDA;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_in, elements, n * 96, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_g1_normalize<<<div_up(n, 64), 64, 0, ctx->stream>>>((const jac_t*)d_in, (affine_t*)d_out, n);
+        ctx->launches += 1;
+        e = cudaMemcpyAsync(affine_out, d_out, n * 64, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) {
+        set_last_error(cudaGetErrorString(e));
+        return BBG_ERR_CUDA;
+    }
+    return BBG_OK;
+}
+
 int bbg_g1_op(int op, const void* a, const void* b, void* out, size_t n)
 {
     GET_CTX();
+    StreamScope order(ctx, ctx->stream);
     if (n == 0) return BBG_OK;
     const size_t bsz = op == 0 ? 64 : 96;
     void *da = nullptr, *db = nullptr, *dout = nullptr;

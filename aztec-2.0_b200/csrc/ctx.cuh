@@ -77,16 +77,37 @@ struct Profiler {
     }
 };
 
+// Everything one MSM in flight needs.  The context owns two, so that a batch (bbg_msm_batch) can run MSM i + 1 on a
+// second stream while the latency-bound tail of MSM i (slot merge, bucket reduction) is still draining.
+struct MsmWorkspace {
+    DevBuf scalars, counts, offsets, cursors, sorted, buckets, partials, reduce, scan_tmp, result, lvl_offsets, pairs_a, pairs_b,
+        pair_pre, pair_meta, pts0;
+    void release()
+    {
+        DevBuf* all[] = { &scalars, &counts, &offsets, &cursors, &sorted, &buckets, &partials, &reduce, &scan_tmp, &result,
+                          &lvl_offsets, &pairs_a, &pairs_b, &pair_pre, &pair_meta, &pts0 };
+        for (DevBuf* b : all) b->release();
+    }
+};
+
 struct Context {
     int device = -1;
     int num_sms = 148;
     cudaStream_t stream = nullptr; // default work stream for the host-pointer entry points
     cudaStream_t copy_stream = nullptr; // H2D pieces that overlap with kernels on `stream`
+    cudaStream_t aux_stream = nullptr;  // second work stream of the batched entry points
     cudaEvent_t ev_piece[8] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Cross-stream ordering of the shared workspaces and cached tables: every call records `last_use` on its stream when
+    // it has queued its work, and a call on a DIFFERENT stream first waits for it (StreamScope in internal.hpp).  Calls on
+    // different streams therefore serialise on the device; they never race on the workspaces.
+    cudaEvent_t last_use = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
     // MSM workspaces
-    DevBuf msm_scalars, msm_counts, msm_offsets, msm_cursors, msm_sorted, msm_buckets, msm_partials, msm_reduce,
-        msm_scan_tmp, msm_result, msm_points, msm_lvl_offsets, msm_pairs_a, msm_pairs_b, msm_pair_pre, msm_pair_meta, msm_pts0;
+    MsmWorkspace msm_ws[2];
+    DevBuf msm_points;
     void* inv_fix_fq = nullptr; // inv.cuh fix-up constants (fq)
     // NTT workspaces
     DevBuf ntt_data, ntt_scratch, ntt_pro, ntt_epi, ntt_small;
@@ -102,9 +123,30 @@ struct Context {
     std::vector<ScaleTab> ntt_scale_cache;
     uint64_t ntt_scale_clock = 0;
     void* ntt_stage_tw[2] = { nullptr, nullptr }; // per-direction small stage-twiddle tables
-    // pinned staging for small results
-    void* pinned = nullptr;
-    size_t pinned_cap = 0;
+    bool ntt_attr_set = false;                    // cudaFuncSetAttribute done for this context's device
+    size_t ntt_table_bytes = 0;                   // bytes held by ntt_twiddles + ntt_scale_cache (budget: ntt.cu)
+    std::map<unsigned, uint64_t> ntt_twiddle_use; // log2n -> last-use clock (LRU eviction together with the scale tables)
+    // pointwise / scan workspaces (poly.cu)
+    DevBuf poly_tmp;
+    // Resident polynomials (resident.cu): device mirrors of caller-owned host arrays, keyed by host address, so that a
+    // chain of calls on the same array (ifft -> commitment MSM -> coset FFT) crosses PCIe once.  Off unless enabled.
+    struct Resident {
+        const char* host = nullptr;
+        size_t bytes = 0;    // extent of the host array mirrored
+        void* d = nullptr;
+        size_t cap = 0;
+        bool host_stale = false; // the device copy is newer than host memory (write-back deferred)
+        uint64_t last_use = 0;
+        static constexpr int SAMPLES = 72;
+        uint32_t n_samples = 0;
+        uint64_t sample_off[SAMPLES]; // byte offsets of the fingerprint words
+        uint64_t sample_val[SAMPLES];
+    };
+    std::vector<Resident> resident;
+    int resident_mode = -1; // -1: read BBG_RESIDENT on first use; 0 off; 1 on
+    size_t resident_bytes = 0, resident_budget = 0;
+    uint64_t resident_clock = 0;
+    uint64_t resident_hits = 0, resident_misses = 0, resident_h2d_saved = 0;
     Profiler prof;
     uint64_t launches = 0; // kernels launched by this library (bench.py reports it)
     double last_kernel_ms = 0.0;

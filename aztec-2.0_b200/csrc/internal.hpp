@@ -5,6 +5,23 @@
 
 namespace bbg {
 
+// Orders a call that uses the context's shared workspaces / cached tables on stream `st` after the previous call if that
+// one ran on a different stream (see Context::last_use).  Construct before queueing any work, destroy after the last launch.
+struct StreamScope {
+    Context* c;
+    cudaStream_t st;
+    StreamScope(Context* ctx, cudaStream_t s) : c(ctx), st(s)
+    {
+        if (c->last_valid && c->last_stream != st) cudaStreamWaitEvent(st, c->last_use, 0);
+    }
+    ~StreamScope()
+    {
+        cudaEventRecord(c->last_use, st);
+        c->last_stream = st;
+        c->last_valid = true;
+    }
+};
+
 // msm.cu
 // Fixed-base levels of a Pippenger object: entry l * stride + i holds 2^(D l) * P_i.  L == 1: plain points.
 struct MsmLevels {
@@ -22,12 +39,27 @@ struct MsmArrival {
     size_t count = 0;
     size_t piece = 0;
 };
-int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_points, size_t point_stride, const MsmLevels& lv,
-               size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival = nullptr);
+int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, const void* d_points, size_t point_stride,
+               const MsmLevels& lv, size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival = nullptr);
 int g1_sum_device(Context* ctx, const void* d_jacs, size_t n, void* d_out, cudaStream_t st);
 int srs_decode_device(Context* ctx, const void* d_raw, size_t n, void* d_points, cudaStream_t st);
 int point_table_device(Context* ctx, const void* d_points, size_t n, void* d_table, cudaStream_t st);
 int compact_even_device(Context* ctx, const void* d_table, size_t n, void* d_points, cudaStream_t st);
+
+// resident.cu -- device mirrors of host arrays (see Context::Resident)
+bool resident_enabled(Context* ctx);
+// Device address mirroring host bytes [host, host + bytes).  need_data: the device copy must hold the host content on return
+// (queued on `st`): served from a valid mirror, else uploaded.  *hit tells which.  With residency off this returns
+// BBG_OK and *d_out = nullptr: the caller uses its own staging buffer.
+int resident_acquire(Context* ctx, const void* host, size_t bytes, bool need_data, void** d_out, bool* hit, cudaStream_t st);
+// The device mirror of [host, host + bytes) was just (re)written on `st`.  write_back: copy it to the host array now
+// (synchronises `st`) and re-fingerprint; otherwise the host copy is marked stale until resident_flush.
+int resident_commit(Context* ctx, const void* host, size_t bytes, bool write_back, cudaStream_t st);
+// The host array [host, host + bytes) was written by the caller (or will be): drop / refresh mirrors overlapping it.
+void resident_invalidate(Context* ctx, const void* host, size_t bytes);
+// Write every stale mirror overlapping [host, host + bytes) back to host memory (bytes == 0: all of them).
+int resident_flush(Context* ctx, const void* host, size_t bytes, cudaStream_t st);
+void resident_clear(Context* ctx);
 
 // ntt.cu
 struct NttScale {

@@ -33,11 +33,15 @@
 // traffic is ~(32 + 68*W) B per point.  No kernel calls a non-inlined device function (see g1.cuh).
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "g1.cuh"
 #include "internal.hpp"
 #include "inv.cuh"
 
 namespace bbg {
+
+namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------------
 // 1/3. digits: histogram (SCATTER = false) or counting-sort scatter (SCATTER = true)
@@ -631,21 +635,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2) k_msm_pair_pass(const uint32_
 
 // One merge level: worker u folds slots [u*K + 1, (u+1)*K + 1) (worker 0 also takes slot 0), i.e. the
 // boundary falls between the two slots of one chunk so the typical (tail, next head) pair is never cut.
-__global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
-                                                    uint32_t n_in,
-                                                    uint32_t workers,
-                                                    const uint32_t* __restrict__ pending_in,
-                                                    xyzz_t* __restrict__ buckets,
-                                                    Slot* __restrict__ out,
-                                                    uint32_t* __restrict__ pending_out)
+__device__ __forceinline__ void merge_worker(const Slot* __restrict__ in, uint32_t n_in, uint32_t workers, uint32_t u,
+                                             xyzz_t* __restrict__ buckets, Slot* __restrict__ out, uint32_t* __restrict__ pending_out)
 {
-    if (__ldg(pending_in) == 0) {
-        return; // the previous level left nothing open (the usual case after the first merge)
-    }
-    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= workers) {
-        return;
-    }
     const uint32_t lo = u == 0 ? 0 : u * MERGE_K + 1;
     uint32_t hi = (u + 1) * MERGE_K + 1;
     if (hi > n_in || u + 1 == workers) hi = n_in;
@@ -691,6 +683,55 @@ __global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
     if (!b_set) out_b->bucket = SLOT_NONE;
     if (a_set || b_set) {
         atomicAdd(pending_out, 1u);
+    }
+}
+
+// level 0: one worker per thread over the 2 * num_chunks slots the accumulation left
+__global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
+                                                    uint32_t n_in,
+                                                    uint32_t workers,
+                                                    const uint32_t* __restrict__ pending_in,
+                                                    xyzz_t* __restrict__ buckets,
+                                                    Slot* __restrict__ out,
+                                                    uint32_t* __restrict__ pending_out)
+{
+    if (__ldg(pending_in) == 0) {
+        return; // no bucket was cut by a chunk boundary
+    }
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= workers) {
+        return;
+    }
+    merge_worker(in, n_in, workers, u, buckets, out, pending_out);
+}
+
+// levels 1..: ONE cooperative launch loops over the remaining levels with a grid barrier in between and stops at the
+// first level that has nothing open -- for uniform scalars that is immediately (a bucket would have to span more than
+// MERGE_K / 2 chunks), so the round-1 chain of up to 13 early-exit launches (~3 us each) is gone; when every scalar is
+// equal the loop still runs the full log-depth merge.
+__global__ void __launch_bounds__(128) k_msm_merge_rest(Slot* __restrict__ slots, uint32_t n_in, uint32_t* __restrict__ pending,
+                                                         xyzz_t* __restrict__ buckets)
+{
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    Slot* in = slots;
+    for (uint32_t level = 1; level < 15; ++level) {
+        if (*(volatile uint32_t*)(pending + level) == 0) {
+            break; // uniform: every thread reads the same counter after the barrier
+        }
+        const uint32_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
+        Slot* out = in + n_in;
+        for (uint32_t u = tid; u < workers; u += nthreads) {
+            merge_worker(in, n_in, workers, u, buckets, out, pending + level + 1);
+        }
+        __threadfence();
+        grid.sync();
+        if (workers == 1) {
+            break;
+        }
+        in = out;
+        n_in = 2 * workers;
     }
 }
 
@@ -1006,17 +1047,17 @@ __global__ void __launch_bounds__(256) k_compact_even(const uint4* __restrict__ 
 // host orchestration
 // ------------------------------------------------------------------------------------------------
 // rows >= 1: row y of d_out (n + 1 entries each) = exclusive scan of ceil(d_in / 2^(shift_base + y))
-static int exclusive_scan(Context* ctx, const uint32_t* d_in, size_t n, uint32_t* d_out, uint32_t* d_out_copy, cudaStream_t st,
-                          unsigned rows = 1, unsigned shift_base = 0)
+static int exclusive_scan(Context* ctx, MsmWorkspace& ws, const uint32_t* d_in, size_t n, uint32_t* d_out, uint32_t* d_out_copy,
+                          cudaStream_t st, unsigned rows = 1, unsigned shift_base = 0)
 {
     unsigned tiles = div_up(n, SCAN_TILE);
     if (tiles > SCAN_TILE) {
         set_last_error("scan too large");
         return BBG_ERR_ARG;
     }
-    int rc = ctx->msm_scan_tmp.reserve((size_t)rows * SCAN_TILE * 4 + 16);
+    int rc = ws.scan_tmp.reserve((size_t)rows * SCAN_TILE * 4 + 16);
     if (rc) return rc;
-    uint32_t* tmp = (uint32_t*)ctx->msm_scan_tmp.p;
+    uint32_t* tmp = (uint32_t*)ws.scan_tmp.p;
     k_scan_tile_sums<<<dim3(tiles, rows), SCAN_THREADS, 0, st>>>(d_in, n, tmp, shift_base);
     k_scan_top<<<dim3(1, rows), SCAN_THREADS, 0, st>>>(tmp, tiles);
     k_scan_apply<<<dim3(tiles, rows), SCAN_THREADS, 0, st>>>(d_in, n, tmp, d_out, d_out_copy, shift_base);
@@ -1101,8 +1142,8 @@ int msm_precompute_device(Context* ctx, void* d_table, size_t n, const MsmLevels
 
 // Device-pointer MSM over table entries [base, base + n) of level 0 (and the same range of every other level).
 //   lv.L == 1: plain points (any stride), W bucket sets.   lv.L > 1: fixed-base levels, S = D / c bucket sets.
-int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_points, size_t point_stride, const MsmLevels& lv_in,
-               size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival)
+int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, const void* d_points, size_t point_stride,
+               const MsmLevels& lv_in, size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival)
 {
     Profiler& pr = ctx->prof;
     pr.begin();
@@ -1115,7 +1156,9 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     MsmLevels lv = lv_in;
     if (lv.L <= 1) {
         lv.L = 1;
-        lv.c = env_uint("BBG_MSM_C1", (unsigned)std::max(2, std::min(16, (int)floor_log2(n) - 4)));
+        // plain points: W bucket sets of 2^(c-1) buckets and a 255-doubling Horner at the end whatever c is; windows narrower
+        // than 8 bits only add Horner additions (the verifier's 27-point MSMs ran with c = 2: 128 sets, 128 additions)
+        lv.c = env_uint("BBG_MSM_C1", (unsigned)std::max(8, std::min(16, (int)floor_log2(n) - 4)));
         lv.stride = 0;
     }
     const unsigned c = lv.c;
@@ -1129,16 +1172,16 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
         return BBG_ERR_ARG;
     }
     int rc;
-    if ((rc = ctx->msm_counts.reserve((G + 1) * 4 + 64))) return rc;
-    if ((rc = ctx->msm_offsets.reserve((G + 1) * 4))) return rc;
-    if ((rc = ctx->msm_cursors.reserve((G + 1) * 4))) return rc;
-    if ((rc = ctx->msm_sorted.reserve(max_entries * 4))) return rc;
-    if ((rc = ctx->msm_buckets.reserve(G * sizeof(xyzz_t)))) return rc;
-    uint32_t* counts = (uint32_t*)ctx->msm_counts.p;
-    uint32_t* offsets = (uint32_t*)ctx->msm_offsets.p;
-    uint32_t* cursors = (uint32_t*)ctx->msm_cursors.p;
-    uint32_t* sorted = (uint32_t*)ctx->msm_sorted.p;
-    xyzz_t* buckets = (xyzz_t*)ctx->msm_buckets.p;
+    if ((rc = ws.counts.reserve((G + 1) * 4 + 64))) return rc;
+    if ((rc = ws.offsets.reserve((G + 1) * 4))) return rc;
+    if ((rc = ws.cursors.reserve((G + 1) * 4))) return rc;
+    if ((rc = ws.sorted.reserve(max_entries * 4))) return rc;
+    if ((rc = ws.buckets.reserve(G * sizeof(xyzz_t)))) return rc;
+    uint32_t* counts = (uint32_t*)ws.counts.p;
+    uint32_t* offsets = (uint32_t*)ws.offsets.p;
+    uint32_t* cursors = (uint32_t*)ws.cursors.p;
+    uint32_t* sorted = (uint32_t*)ws.sorted.p;
+    xyzz_t* buckets = (xyzz_t*)ws.buckets.p;
     uint32_t* pending = counts + G + 1; // 15 merge-level counters behind the histogram (zeroed with it)
 
     pr.mark(st, PH_MSM_DIGITS);
@@ -1180,7 +1223,7 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
         ctx->launches += 1;
     }
     pr.mark(st, PH_MSM_SCAN);
-    if ((rc = exclusive_scan(ctx, counts, G, offsets, cursors, st))) return rc;
+    if ((rc = exclusive_scan(ctx, ws, counts, G, offsets, cursors, st))) return rc;
     // ---- optional pairwise affine passes (k_msm_pair_pass): J levels, each halving every bucket's entry count.
     // OFF by default: measured on B200 (2^20 points, c = 17) the passes take 3.6-4.2 ms against 2.47 ms for the
     // projective accumulation below -- 5.8 instead of 10 multiplies per addition, but two dependent sweeps over
@@ -1194,8 +1237,8 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     pr.mark(st, PH_MSM_SCATTER);
     affine_t* pts0 = nullptr;
     if (materialise) {
-        if ((rc = ctx->msm_pts0.reserve(max_entries * sizeof(affine_t)))) return rc;
-        pts0 = (affine_t*)ctx->msm_pts0.p;
+        if ((rc = ws.pts0.reserve(max_entries * sizeof(affine_t)))) return rc;
+        pts0 = (affine_t*)ws.pts0.p;
         k_msm_digits<DIG_SCATTER_POINTS><<<dig_blocks, 256, 0, st>>>((const fr_t*)d_scalars, dp, cursors, nullptr,
                                                                       (const affine_t*)d_points, (uint32_t)point_stride, pts0);
     } else {
@@ -1208,23 +1251,23 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     size_t acc_entries = max_entries;
     if (J > 0) {
         if ((rc = ensure_inv_fix(ctx))) return rc;
-        if ((rc = ctx->msm_lvl_offsets.reserve((size_t)J * (G + 1) * 4))) return rc;
-        uint32_t* lvl = (uint32_t*)ctx->msm_lvl_offsets.p; // row j-1: offsets of level j
-        if ((rc = exclusive_scan(ctx, counts, G, lvl, nullptr, st, J, 1))) return rc;
+        if ((rc = ws.lvl_offsets.reserve((size_t)J * (G + 1) * 4))) return rc;
+        uint32_t* lvl = (uint32_t*)ws.lvl_offsets.p; // row j-1: offsets of level j
+        if ((rc = exclusive_scan(ctx, ws, counts, G, lvl, nullptr, st, J, 1))) return rc;
         // worst-case entry counts per level: sum_b ceil(m_b / 2) <= (E + G) / 2
         size_t e_max[13];
         e_max[0] = max_entries;
         for (unsigned j = 1; j <= J; ++j) e_max[j] = std::min(e_max[j - 1], (e_max[j - 1] + G + 1) / 2);
-        if ((rc = ctx->msm_pairs_a.reserve(e_max[1] * sizeof(affine_t)))) return rc;
-        if (J > 1 && (rc = ctx->msm_pairs_b.reserve(e_max[2] * sizeof(affine_t)))) return rc;
-        if ((rc = ctx->msm_pair_pre.reserve(e_max[1] * 32))) return rc;
-        if ((rc = ctx->msm_pair_meta.reserve(e_max[1] * 8))) return rc;
+        if ((rc = ws.pairs_a.reserve(e_max[1] * sizeof(affine_t)))) return rc;
+        if (J > 1 && (rc = ws.pairs_b.reserve(e_max[2] * sizeof(affine_t)))) return rc;
+        if ((rc = ws.pair_pre.reserve(e_max[1] * 32))) return rc;
+        if ((rc = ws.pair_meta.reserve(e_max[1] * 8))) return rc;
         const unsigned k_force = std::min<unsigned>(PAIR_K_MAX, env_uint("BBG_MSM_PAIR_K", 0)); // 0: choose per level
         pr.mark(st, PH_MSM_PAIRS);
         const affine_t* in = pts0;
         const uint32_t* off_in = offsets;
         for (unsigned j = 1; j <= J; ++j) {
-            affine_t* out = (affine_t*)((j & 1) ? ctx->msm_pairs_a.p : ctx->msm_pairs_b.p);
+            affine_t* out = (affine_t*)((j & 1) ? ws.pairs_a.p : ws.pairs_b.p);
             const uint32_t* off_out = lvl + (size_t)(j - 1) * (G + 1);
             // slots per thread: as many as amortise the inversion, but keep >= ~4 CTAs per SM in the grid
             unsigned K = (unsigned)(e_max[j] / ((size_t)PAIR_THREADS * ctx->num_sms * 4));
@@ -1233,11 +1276,11 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
             if (j == 1 && !materialise) {
                 k_msm_pair_pass<true><<<blocks, PAIR_THREADS, 0, st>>>(
                     sorted, (const affine_t*)d_points, (uint32_t)point_stride, off_in, off_out, (uint32_t)G, out,
-                    (const uint32_t*)ctx->inv_fix_fq, K, (uint4*)ctx->msm_pair_pre.p, (uint2*)ctx->msm_pair_meta.p);
+                    (const uint32_t*)ctx->inv_fix_fq, K, (uint4*)ws.pair_pre.p, (uint2*)ws.pair_meta.p);
             } else {
                 k_msm_pair_pass<false><<<blocks, PAIR_THREADS, 0, st>>>(nullptr, in, 1, off_in, off_out, (uint32_t)G, out,
                                                                         (const uint32_t*)ctx->inv_fix_fq, K,
-                                                                        (uint4*)ctx->msm_pair_pre.p, (uint2*)ctx->msm_pair_meta.p);
+                                                                        (uint4*)ws.pair_pre.p, (uint2*)ws.pair_meta.p);
             }
             ctx->launches += 1;
             in = out;
@@ -1268,8 +1311,8 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
             n_in = 2 * workers;
         }
     }
-    if ((rc = ctx->msm_partials.reserve(slots_total * sizeof(Slot)))) return rc;
-    Slot* slots = (Slot*)ctx->msm_partials.p;
+    if ((rc = ws.partials.reserve(slots_total * sizeof(Slot)))) return rc;
+    Slot* slots = (Slot*)ws.partials.p;
 
     pr.mark(st, PH_MSM_ACCUMULATE);
     if (J > 0) {
@@ -1283,19 +1326,25 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
     ctx->launches += 1;
     pr.mark(st, PH_MSM_FIXUP);
     {
-        size_t n_in = 2 * num_chunks;
-        Slot* in = slots;
-        unsigned level = 0;
-        while (level < 14) {
-            const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
-            Slot* out = in + n_in;
-            k_msm_merge<<<div_up(workers, 128), 128, 0, st>>>(in, (uint32_t)n_in, (uint32_t)workers, pending + level, buckets, out,
-                                                             pending + level + 1);
+        const size_t n_in = 2 * num_chunks;
+        const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
+        Slot* out = slots + n_in;
+        k_msm_merge<<<div_up(workers, 128), 128, 0, st>>>(slots, (uint32_t)n_in, (uint32_t)workers, pending, buckets, out, pending + 1);
+        ctx->launches += 1;
+        if (workers > 1) {
+            static int ctas_per_sm = 0; // occupancy of the cooperative kernel (all of its CTAs must be co-resident)
+            if (ctas_per_sm == 0) {
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_msm_merge_rest, 128, 0) != cudaSuccess || ctas_per_sm < 1) {
+                    ctas_per_sm = 1;
+                }
+            }
+            const uint32_t workers1 = (uint32_t)((2 * workers - 1 + MERGE_K - 1) / MERGE_K);
+            const unsigned grid = std::max(1u, std::min<unsigned>(div_up(workers1, 128), (unsigned)(ctx->num_sms * ctas_per_sm)));
+            Slot* lvl1_in = out;
+            uint32_t lvl1_n = (uint32_t)(2 * workers);
+            void* args[] = { (void*)&lvl1_in, (void*)&lvl1_n, (void*)&pending, (void*)&buckets };
+            BBG_CUDA(cudaLaunchCooperativeKernel((const void*)k_msm_merge_rest, dim3(grid), dim3(128), args, 0, st));
             ctx->launches += 1;
-            ++level;
-            if (workers == 1) break;
-            in = out;
-            n_in = 2 * workers;
         }
     }
 
@@ -1323,8 +1372,8 @@ int msm_device(Context* ctx, const void* d_scalars, size_t n, const void* d_poin
         const uint32_t parts = std::min<uint32_t>(2 * TREE_THREADS, std::max<uint32_t>(1, segs0 / (2 * TREE_THREADS)));
         const size_t n_rows = (size_t)levels * S;
         // layout: R0 | V1 | T0 | per-part sums | per-row sums
-        if ((rc = ctx->msm_reduce.reserve(((total_segs + segs0) * S + n_rows * parts + n_rows) * sizeof(xyzz_t)))) return rc;
-        xyzz_t* r_all = (xyzz_t*)ctx->msm_reduce.p;
+        if ((rc = ws.reduce.reserve(((total_segs + segs0) * S + n_rows * parts + n_rows) * sizeof(xyzz_t)))) return rc;
+        xyzz_t* r_all = (xyzz_t*)ws.reduce.p;
         xyzz_t* t0 = r_all + total_segs * S;
         xyzz_t* part_out = t0 + (size_t)segs0 * S;
         xyzz_t* row_out = part_out + n_rows * parts;

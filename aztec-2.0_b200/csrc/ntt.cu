@@ -526,8 +526,65 @@ static int ensure_stage_tables(Context* ctx, cudaStream_t st)
     return BBG_OK;
 }
 
+// ---- cached tables (w_N^e per size, geometric scaling tables) share ONE byte budget with LRU eviction across both kinds,
+// so a run of large coset transforms cannot crowd out the MSM workspaces (each table is up to 32 N bytes).
+static size_t ntt_table_budget()
+{
+    static const size_t budget = [] {
+        const char* v = getenv("BBG_NTT_TABLE_MAX_MB");
+        if (v && *v) return (size_t)atoll(v) << 20;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) total_b = (size_t)64 << 30;
+        return std::max<size_t>(total_b / 12, (size_t)1 << 30); // 15 GB of a B200's 180 GB
+    }();
+    return budget;
+}
+// frees least-recently-used tables until `need` more bytes fit; `keep_log_n` / `keep_tab` are in use by the caller
+static void ntt_tables_make_room(Context* ctx, size_t need, unsigned keep_log_n, const void* keep_tab)
+{
+    const size_t budget = ntt_table_budget();
+    while (ctx->ntt_table_bytes + need > budget) {
+        // oldest of both kinds
+        uint64_t best = ~0ull;
+        int kind = -1;
+        unsigned tw_key = 0;
+        size_t sc_idx = 0;
+        for (auto& kv : ctx->ntt_twiddles) {
+            if (kv.first == keep_log_n) continue;
+            const uint64_t u = ctx->ntt_twiddle_use[kv.first];
+            if (u < best) {
+                best = u;
+                kind = 0;
+                tw_key = kv.first;
+            }
+        }
+        for (size_t i = 0; i < ctx->ntt_scale_cache.size(); ++i) {
+            const auto& e = ctx->ntt_scale_cache[i];
+            if (e.tab == nullptr || e.tab == keep_tab) continue;
+            if (e.last_use < best) {
+                best = e.last_use;
+                kind = 1;
+                sc_idx = i;
+            }
+        }
+        if (kind < 0) return; // nothing left to evict
+        if (kind == 0) {
+            cudaFree(ctx->ntt_twiddles[tw_key]); // cudaFree synchronises with any kernel still reading the table
+            ctx->ntt_table_bytes -= sizeof(fr) << tw_key;
+            ctx->ntt_twiddles.erase(tw_key);
+            ctx->ntt_twiddle_use.erase(tw_key);
+        } else {
+            auto& e = ctx->ntt_scale_cache[sc_idx];
+            cudaFree(e.tab);
+            ctx->ntt_table_bytes -= e.count * sizeof(fr);
+            ctx->ntt_scale_cache.erase(ctx->ntt_scale_cache.begin() + (long)sc_idx);
+        }
+    }
+}
+
 static int ensure_big_table(Context* ctx, unsigned log_n, const fr** out, cudaStream_t st)
 {
+    ctx->ntt_twiddle_use[log_n] = ++ctx->ntt_scale_clock;
     auto it = ctx->ntt_twiddles.find(log_n);
     if (it != ctx->ntt_twiddles.end()) {
         *out = (const fr*)it->second;
@@ -535,10 +592,12 @@ static int ensure_big_table(Context* ctx, unsigned log_n, const fr** out, cudaSt
     }
     fr* tab = nullptr;
     const uint64_t N = 1ull << log_n;
+    ntt_tables_make_room(ctx, N * sizeof(fr), log_n, nullptr);
     BBG_CUDA(cudaMalloc(&tab, N * sizeof(fr)));
     int rc = launch_powers(ctx, tab, N, ntt_root_of_unity(log_n), hf::one(), 0, st);
     if (rc) return rc;
     ctx->ntt_twiddles[log_n] = tab;
+    ctx->ntt_table_bytes += N * sizeof(fr);
     *out = tab;
     return BBG_OK;
 }
@@ -547,10 +606,11 @@ static int ensure_big_table(Context* ctx, unsigned log_n, const fr** out, cudaSt
 // is new (first sighting), too large, or the build failed; the caller then uses the two-level tables.
 static constexpr uint64_t NTT_SCALE_MAX_BYTES = 1ull << 30;  // per table
 static constexpr size_t NTT_SCALE_MAX_TABLES = 8;
-static int get_scale_table(Context* ctx, uint64_t count, const hf::Fr& start, const hf::Fr& shift, const fr** out, cudaStream_t st)
+static int get_scale_table(Context* ctx, uint64_t count, const hf::Fr& start, const hf::Fr& shift, const fr** out, cudaStream_t st,
+                           unsigned cur_log_n)
 {
     *out = nullptr;
-    if (count == 0 || count * sizeof(fr) > NTT_SCALE_MAX_BYTES) return BBG_OK;
+    if (count == 0 || count * sizeof(fr) > NTT_SCALE_MAX_BYTES || count * sizeof(fr) > ntt_table_budget() / 4) return BBG_OK;
     static const bool disabled = [] {
         const char* v = getenv("BBG_NTT_NO_SCALE_CACHE");
         return v && *v && atoi(v) != 0;
@@ -558,10 +618,20 @@ static int get_scale_table(Context* ctx, uint64_t count, const hf::Fr& start, co
     if (disabled) return BBG_OK;
     auto& cache = ctx->ntt_scale_cache;
     const uint64_t now = ++ctx->ntt_scale_clock;
-    for (auto& e : cache) {
+    for (size_t idx = 0; idx < cache.size(); ++idx) {
+        auto& e = cache[idx];
         if (e.count == count && memcmp(e.start, start.d, 32) == 0 && memcmp(e.shift, shift.d, 32) == 0) {
             e.last_use = now;
             if (e.tab == nullptr) {
+                uint64_t key_start[4], key_shift[4];
+                memcpy(key_start, e.start, 32);
+                memcpy(key_shift, e.shift, 32);
+                ntt_tables_make_room(ctx, count * sizeof(fr), cur_log_n, nullptr); // may reshuffle `cache`: look the key up again
+                Context::ScaleTab* ep = nullptr;
+                for (auto& f : cache) {
+                    if (f.count == count && memcmp(f.start, key_start, 32) == 0 && memcmp(f.shift, key_shift, 32) == 0) ep = &f;
+                }
+                if (ep == nullptr) return BBG_OK;
                 fr* tab = nullptr;
                 if (cudaMalloc(&tab, count * sizeof(fr)) != cudaSuccess) {
                     cudaGetLastError(); // out of memory: keep using the two-level path
@@ -572,7 +642,10 @@ static int get_scale_table(Context* ctx, uint64_t count, const hf::Fr& start, co
                     cudaFree(tab);
                     return rc;
                 }
-                e.tab = tab;
+                ep->tab = tab;
+                ctx->ntt_table_bytes += count * sizeof(fr);
+                *out = (const fr*)tab;
+                return BBG_OK;
             }
             *out = (const fr*)e.tab;
             return BBG_OK;
@@ -583,7 +656,10 @@ static int get_scale_table(Context* ctx, uint64_t count, const hf::Fr& start, co
         for (size_t i = 1; i < cache.size(); ++i) {
             if (cache[i].last_use < cache[victim].last_use) victim = i;
         }
-        if (cache[victim].tab) cudaFree(cache[victim].tab); // synchronises with any kernel still reading it
+        if (cache[victim].tab) {
+            cudaFree(cache[victim].tab); // synchronises with any kernel still reading it
+            ctx->ntt_table_bytes -= cache[victim].count * sizeof(fr);
+        }
         cache.erase(cache.begin() + (long)victim);
     }
     Context::ScaleTab e;
@@ -667,16 +743,16 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
     const uint64_t lo_count = 1ull << split, hi_count = 1ull << (log_n - split);
     const fr *pro_full = nullptr, *epi_full = nullptr, *tw_scaled = nullptr;
     if (pro.present && rb == 0) {
-        if ((rc = get_scale_table(ctx, std::min<uint64_t>(pro.size, N), pro.start, pro.has_shift ? pro.shift : hf::one(), &pro_full, st))) return rc;
+        if ((rc = get_scale_table(ctx, std::min<uint64_t>(pro.size, N), pro.start, pro.has_shift ? pro.shift : hf::one(), &pro_full, st, log_n))) return rc;
     }
     if (epi.present && epi.has_shift && rb == 0) {
-        if ((rc = get_scale_table(ctx, N, epi.start, epi.shift, &epi_full, st))) return rc;
+        if ((rc = get_scale_table(ctx, N, epi.start, epi.shift, &epi_full, st, log_n))) return rc;
     }
     if (epi.present && !epi.has_shift && rb == 0 && inverse) {
         // plain ifft: fold 1/n into the last inter-pass twiddle (table 1/n * w^e, indexed by the forward exponent)
         const hf::Fr n_inv = hf::invert(hf::from_u64(N));
         if (memcmp(hf::reduce(epi.start).d, hf::reduce(n_inv).d, 32) == 0) {
-            if ((rc = get_scale_table(ctx, N, hf::reduce(n_inv), ntt_root_of_unity(log_n), &tw_scaled, st))) return rc;
+            if ((rc = get_scale_table(ctx, N, hf::reduce(n_inv), ntt_root_of_unity(log_n), &tw_scaled, st, log_n))) return rc;
         }
     }
     if (pro.present && pro_full == nullptr) {
@@ -699,12 +775,11 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         epi_hi = hi;
     }
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->ntt_attr_set) { // per context: a re-init on another device needs the attributes again
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<3>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<1>::SMEM_BYTES));
-        attr_set = true;
+        ctx->ntt_attr_set = true;
     }
     // elements per thread (see NttGeom): 2^loge.  Measured on B200 (fft, ms; E = 2 / 4 / 8): 2^16 0.039 / 0.052 / 0.102 (the grid is
     // only n / (256 E) CTAs there), 2^18 0.091 / 0.088 / 0.116, 2^20 0.249 / 0.241 / 0.287, 2^22 0.948 / 0.892 / 0.948,

@@ -34,6 +34,8 @@ EXPORTS = [
     "bbg_read_g1_elements_from_buffer", "bbg_ntt", "bbg_ntt_dev", "bbg_coset_fft_ext", "bbg_coset_fft_ext_dev",
     "bbg_new_evaluation_domain", "bbg_delete_evaluation_domain", "bbg_ifft", "bbg_coset_fft_with_generator_shift",
     "bbg_domain_constants", "bbg_field_op", "bbg_g1_op",
+    "bbg_pippenger_unsafe_batch", "bbg_pippenger_unsafe_batch_dev", "bbg_pippenger_batch",
+    "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
 ]
 
 
@@ -102,7 +104,16 @@ lib.bbg_pippenger_bind_host_table.argtypes = [_vp, _vp]
 lib.bbg_set_auto_adopt.argtypes = [_int]
 lib.bbg_bench_field_mul.argtypes = [_int, _int, _vp]
 lib.bbg_g1_add_affine_dev.argtypes = [_vp, _vp, _sz, _vp, _vp]
-NUM_PHASES = 12
+lib.bbg_pippenger_unsafe_batch.argtypes = [_vp, _vp, _sz, _sz, _sz, _vp]
+lib.bbg_pippenger_unsafe_batch_dev.argtypes = [_vp, _vp, _sz, _sz, _sz, _vp, _vp]
+lib.bbg_pippenger_batch.argtypes = [_vp, _sz, _vp, _sz, _vp]
+lib.bbg_field_op_dev.argtypes = [_int, _int, _vp, _vp, _vp, _sz, _vp]
+lib.bbg_g1_normalize.argtypes = [_vp, _sz, _vp]
+lib.bbg_resident_mode.argtypes = [_int]
+lib.bbg_resident_invalidate.argtypes = [_vp, _sz]
+lib.bbg_resident_flush.argtypes = [_vp, _sz]
+lib.bbg_resident_stats.argtypes = [_vp]
+NUM_PHASES = 13
 PHASE_NAMES = ["msm_digits", "msm_scan", "msm_scatter", "msm_pairs", "msm_accumulate", "msm_fixup", "msm_reduce", "msm_combine",
                "ntt_tables", "ntt_pass0", "ntt_pass1", "ntt_pass2", "ntt_pass3"]
 
@@ -275,6 +286,26 @@ class Pippenger:
         _check(lib.bbg_pippenger_unsafe_dev(self.h, scalars.data_ptr(), from_, n, out.data_ptr(), _stream_ptr(stream)))
         return out
 
+    def pippenger_unsafe_batch(self, scalar_arrays, from_=0, range_=None, stream=None):
+        """Several MSMs over monomials [from, from+range) in one call (bbg_pippenger_unsafe_batch).  A list of numpy
+        arrays -> numpy (k, 12); a list of torch CUDA tensors -> torch CUDA uint8 (k, 96), asynchronous on `stream`."""
+        k = len(scalar_arrays)
+        if k == 0:
+            return np.zeros((0, 12), dtype=np.uint64)
+        if isinstance(scalar_arrays[0], np.ndarray) or not hasattr(scalar_arrays[0], "data_ptr"):
+            arrs = [_np(a, 4) for a in scalar_arrays]
+            n = arrs[0].shape[0] if range_ is None else range_
+            ptrs = (ctypes.c_void_p * k)(*[a.ctypes.data for a in arrs])
+            out = np.zeros((k, 12), dtype=np.uint64)
+            _check(lib.bbg_pippenger_unsafe_batch(self.h, ctypes.cast(ptrs, _vp), k, from_, n, out.ctypes.data))
+            return out
+        import torch
+        n = scalar_arrays[0].numel() * scalar_arrays[0].element_size() // 32 if range_ is None else range_
+        ptrs = (ctypes.c_void_p * k)(*[a.data_ptr() for a in scalar_arrays])
+        out = torch.empty((k, 96), dtype=torch.uint8, device=scalar_arrays[0].device)
+        _check(lib.bbg_pippenger_unsafe_batch_dev(self.h, ctypes.cast(ptrs, _vp), k, from_, n, out.data_ptr(), _stream_ptr(stream)))
+        return out
+
     def close(self):
         if self.h:
             lib.bbg_delete_pippenger(self.h)
@@ -292,6 +323,39 @@ def pippenger(scalars, points_table2n, num_points, handle_edge_cases=True):
     out = np.zeros(12, dtype=np.uint64)
     _check(lib.bbg_pippenger(s.ctypes.data if num_points else None, t.ctypes.data if num_points else None, num_points,
                              1 if handle_edge_cases else 0, out.ctypes.data))
+    return out
+
+
+def resident_mode(enable):
+    """Resident polynomials on / off (include/bbg.h); enable < 0 queries."""
+    rc = lib.bbg_resident_mode(int(enable))
+    if enable < 0:
+        return rc
+    _check(rc)
+
+
+def resident_stats():
+    out = (ctypes.c_uint64 * 4)()
+    _check(lib.bbg_resident_stats(ctypes.cast(out, _vp)))
+    return {"hits": int(out[0]), "misses": int(out[1]), "h2d_bytes_saved": int(out[2]), "bytes_resident": int(out[3])}
+
+
+def resident_flush(arr=None):
+    _check(lib.bbg_resident_flush(None if arr is None else arr.ctypes.data, 0 if arr is None else arr.nbytes))
+
+
+def resident_invalidate(arr=None):
+    _check(lib.bbg_resident_invalidate(None if arr is None else arr.ctypes.data, 0 if arr is None else arr.nbytes))
+
+
+def pippenger_batch(scalar_arrays, points_table2n, num_points):
+    """bbg_pippenger_batch: k MSMs over an ADOPTED interleaved table addressed by its host pointer."""
+    k = len(scalar_arrays)
+    arrs = [_np(a, 4) for a in scalar_arrays]
+    t = points_table2n
+    ptrs = (ctypes.c_void_p * max(k, 1))(*[a.ctypes.data for a in arrs])
+    out = np.zeros((k, 12), dtype=np.uint64)
+    _check(lib.bbg_pippenger_batch(ctypes.cast(ptrs, _vp), k, t.ctypes.data, num_points, out.ctypes.data))
     return out
 
 
@@ -419,6 +483,23 @@ def field_op(field, op, a, b=None):
     bb = None if b is None else _np(b, 4)
     out = np.zeros_like(a)
     _check(lib.bbg_field_op(field, op, a.ctypes.data, None if bb is None else bb.ctypes.data, out.ctypes.data, a.shape[0]))
+    return out
+
+
+def field_op_dev(field, op, a, b=None, out=None, stream=None):
+    """bbg_field_op on torch CUDA tensors of 32-byte elements (op 7 = reduce_once: canonical form for comparisons)."""
+    import torch
+    out = torch.empty_like(a) if out is None else out
+    n = a.numel() * a.element_size() // 32
+    _check(lib.bbg_field_op_dev(field, op, a.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(), n, _stream_ptr(stream)))
+    return out
+
+
+def g1_normalize(elements):
+    """g1::affine_element(element) for (n, 12) Jacobian elements -> (n, 8) canonical affine."""
+    e = _np(elements, 12)
+    out = np.zeros((e.shape[0], 8), dtype=np.uint64)
+    _check(lib.bbg_g1_normalize(e.ctypes.data, e.shape[0], out.ctypes.data))
     return out
 
 

@@ -33,7 +33,15 @@ extern "C" {
 #define BBG_ERR_IO 5
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
-int bbg_init(int device);              /* bind the process to a CUDA device (idempotent; -1 = current/0) */
+/* Bind the process to a CUDA device (-1 = the caller's current device).  Idempotent for the same device; returns
+ * BBG_ERR_ARG if the library is already bound to a DIFFERENT device (any earlier call creates the context on the
+ * then-current device).  Every entry point binds that device for its own duration and restores the caller's.
+ *
+ * Streams: the host-pointer entry points run on the library's own stream and return when the result is in host
+ * memory.  The "_dev" entry points queue on the caller's stream and return immediately; they share ONE set of
+ * workspaces and cached tables, so the library orders every call after the previous one with an event when the
+ * streams differ -- calls from different streams are safe but execute one after the other on the device. */
+int bbg_init(int device);
 void bbg_shutdown(void);
 const char* bbg_last_error(void);
 int bbg_device_count(void);
@@ -41,10 +49,11 @@ uint64_t bbg_kernel_launches(void);    /* kernels this library has launched so f
 double bbg_last_device_ms(void);       /* CUDA-event time of the kernels of the last host-pointer call */
 
 /* Per-phase device timing of the LAST compute call (CUDA events on the launching stream; measurement aid
- * for bench.py, no reference counterpart).  Phases: 0 msm digits+histogram, 1 scan, 2 scatter, 3 bucket
- * accumulate, 4 fixup, 5 bucket reduce, 6 window combine, 7 ntt tables, 8..11 ntt pass 0..3.
+ * for bench.py, no reference counterpart).  Phases: 0 msm digits+histogram, 1 scan, 2 scatter, 3 pairwise affine
+ * passes (optional path), 4 bucket accumulate, 5 slot merge, 6 bucket reduce, 7 window combine, 8 ntt tables,
+ * 9..12 ntt pass 0..3.
  * bbg_profile_read synchronises on the recorded events and fills ms[0..n) (0 for phases that did not run). */
-#define BBG_NUM_PHASES 12
+#define BBG_NUM_PHASES 13
 int bbg_profile(int enable);
 int bbg_profile_read(double* ms, int n);
 
@@ -92,6 +101,27 @@ unsigned bbg_pippenger_levels(void* pippenger);
  * scalars: `range` fr elements; result: one g1::element (96 B). */
 int bbg_pippenger_unsafe(void* pippenger, const void* scalars, size_t from, size_t range, void* result);
 int bbg_pippenger_unsafe_dev(void* pippenger, const void* d_scalars, size_t from, size_t range, void* d_result, void* stream);
+
+/* `count` MSMs over the same monomials [from, from+range) in one call: what work_queue::process_queue
+ * (bb/plonk/proof_system/prover/work_queue.hpp:213-243) does item by item for the prover's W_1..W_4 and T_1..T_4
+ * commitments.  scalars[i]: `range` fr elements; results: count x 96 B g1::element.  Consecutive MSMs run on two
+ * streams / two workspaces so the latency-bound tail of one overlaps the bucket accumulation of the next. */
+int bbg_pippenger_unsafe_batch(void* pippenger, const void* const* scalars, size_t count, size_t from, size_t range, void* results);
+int bbg_pippenger_unsafe_batch_dev(void* pippenger, const void* const* d_scalars, size_t count, size_t from, size_t range,
+                                   void* d_results, void* stream);
+/* same, addressed like bbg_pippenger(): by the host address of an adopted 2n interleaved table */
+int bbg_pippenger_batch(const void* const* scalars, size_t count, const void* points_table2n, size_t num_points, void* results);
+
+/* ---- resident polynomials (no reference counterpart; bb/plonk/proof_system/prover/work_queue.hpp:208-282 is the caller
+ * they exist for).  With residency on, the host-pointer entry points keep the device copy of every array they
+ * touch, keyed by host address, and skip the upload when the same array (or a slice of it) comes back: ifft ->
+ * commitment MSM -> coset FFT of one wire polynomial crosses PCIe once.  Every mirror carries a fingerprint of the
+ * host words it was made from (first / last elements + stratified samples) that is re-checked on each use, so an
+ * array the caller rewrote in between is uploaded again.  Off by default (BBG_RESIDENT=1 or bbg_resident_mode(1)). */
+int bbg_resident_mode(int enable);                           /* 1 on, 0 off (flushes and frees), -1 query */
+int bbg_resident_invalidate(const void* host, size_t bytes); /* forget mirrors overlapping the range (bytes 0: all) */
+int bbg_resident_flush(const void* host, size_t bytes);      /* write deferred mirrors back to host memory */
+int bbg_resident_stats(uint64_t* out4);                      /* hits, misses, H2D bytes saved, bytes resident */
 
 /* bb/.../scalar_multiplication.hpp:139-148  pippenger(scalars, points, num_points, state, handle_edge_cases)
  * and pippenger_unsafe(...).  `points` is the 2n interleaved table (even entries are read).  If it lies inside a
@@ -157,6 +187,10 @@ int bbg_domain_constants(size_t n, void* out6);
 /* element-wise probe used by the L0 parity tests: out[i] = op(a[i], b[i]) on the device.
  * field: 0 fq, 1 fr.  op: 0 mul 1 add 2 sub 3 sqr 4 to_montgomery 5 from_montgomery 7 reduce_once 8 neg */
 int bbg_field_op(int field, int op, const void* a, const void* b, void* out, size_t n);
+int bbg_field_op_dev(int field, int op, const void* d_a, const void* d_b, void* d_out, size_t n, void* stream);
+/* g1::affine_element(element) (bb/ecc/groups/element_impl.hpp:51-68) for n Jacobian elements: canonical affine
+ * coordinates (what affine_element::to_buffer() serialises), infinity flag kept */
+int bbg_g1_normalize(const void* elements, size_t n, void* affine_out);
 /* g1 probe: op 0 mixed add (jac, affine) 1 add (jac, jac) 2 dbl (jac); inputs/outputs 96-byte Jacobian */
 int bbg_g1_op(int op, const void* a, const void* b, void* out, size_t n);
 
