@@ -367,6 +367,18 @@ struct DomainObj {
     size_t n;
 };
 
+// one transform of the bb/polynomials/polynomial_arithmetic.hpp:23-39 family on a device array, in place (no locking)
+int ntt_run_kind(Context* ctx, void* d_coeffs, size_t n, int kind, size_t generator_size, const void* constant, cudaStream_t st)
+{
+    unsigned lg;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    bool inverse;
+    NttScale pro, epi;
+    if ((rc = ntt_kind_params(kind, lg, generator_size, constant, inverse, pro, epi))) return rc;
+    return ntt_device(ctx, d_coeffs, d_coeffs, lg, inverse, pro, epi, 0, 0, st);
+}
+
 } // namespace bbg
 
 using namespace bbg;
@@ -414,7 +426,7 @@ void bbg_shutdown(void)
     g_ctx->ntt_scale_cache.clear();
     for (auto& ws : g_ctx->msm_ws) ws.release();
     DevBuf* bufs[] = { &g_ctx->msm_points, &g_ctx->ntt_data, &g_ctx->ntt_scratch, &g_ctx->ntt_pro, &g_ctx->ntt_epi, &g_ctx->ntt_small,
-                       &g_ctx->poly_tmp };
+                       &g_ctx->poly_tmp, &g_ctx->poly_stage };
     for (auto* b : bufs) b->release();
     if (g_ctx->inv_fix_fq) cudaFree(g_ctx->inv_fix_fq);
     for (auto& e : g_ctx->prof.ev) {
@@ -982,9 +994,9 @@ int bbg_ntt_dev(void* d_coeffs, size_t n, int kind, size_t generator_size, const
     return ntt_device(ctx, d_coeffs, d_coeffs, lg, inverse, pro, epi, 0, 0, (cudaStream_t)stream);
 }
 
-int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant)
+// host-pointer transform; keep_on_device: leave the result in the array's device mirror (host copy stale) when it has one
+static int ntt_host(Context* ctx, void* coeffs, size_t n, int kind, size_t generator_size, const void* constant, bool keep_on_device)
 {
-    GET_CTX();
     StreamScope order(ctx, ctx->stream);
     unsigned lg;
     int rc = log2_exact(n, lg);
@@ -995,13 +1007,14 @@ int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void*
     void* d_res = nullptr;
     bool hit = false;
     if ((rc = resident_acquire(ctx, coeffs, n * 32, true, &d_res, &hit, ctx->stream))) return rc;
-    StatScope stat(STAT_NTT, ctx, hit ? 0 : n * 32, n * 32);
+    const bool keep = keep_on_device && d_res != nullptr;
+    StatScope stat(STAT_NTT, ctx, hit ? 0 : n * 32, keep ? 0 : n * 32);
     if (d_res != nullptr) {
         // resident mirror: transform it in place and bring the result home; the mirror stays valid for the next call
         DeviceTimer tm(ctx);
         if ((rc = ntt_device(ctx, d_res, d_res, lg, inverse, pro, epi, 0, 0, ctx->stream))) return rc;
         tm.stop();
-        if ((rc = resident_commit(ctx, coeffs, n * 32, true, ctx->stream))) return rc;
+        if ((rc = resident_commit(ctx, coeffs, n * 32, !keep, ctx->stream))) return rc;
         return tm.finish();
     }
     if ((rc = ctx->ntt_data.reserve(n * 32))) return rc;
@@ -1019,6 +1032,17 @@ static void ntt_factor(unsigned log_n, unsigned& first_bits, unsigned& last_bits
     const unsigned num_passes = log_n <= 16 ? 2 : (log_n <= 24 ? 3 : 4);
     first_bits = log_n / num_passes + (0 < log_n % num_passes ? 1 : 0);
     last_bits = log_n / num_passes + ((num_passes - 1) < log_n % num_passes ? 1 : 0);
+}
+
+int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant)
+{
+    GET_CTX();
+    return ntt_host(ctx, coeffs, n, kind, generator_size, constant, false);
+}
+int bbg_ntt_ex(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant, unsigned flags)
+{
+    GET_CTX();
+    return ntt_host(ctx, coeffs, n, kind, generator_size, constant, (flags & BBG_KEEP_ON_DEVICE) != 0);
 }
 
 int bbg_ntt_dist_layout(size_t n, int world, unsigned* in_pos, unsigned* out_pos)

@@ -35,6 +35,8 @@ struct DeviceGuard {
     ::bbg::DeviceGuard _dg(ctx->device);         \
     std::lock_guard<std::mutex> _lk(ctx->mu)
 
+int ntt_run_kind(Context* ctx, void* d_coeffs, size_t n, int kind, size_t generator_size, const void* constant, cudaStream_t st);
+
 extern Staging g_staging; // pinned staging buffers + copy threads for pageable host memory (staging.hpp)
 
 

@@ -127,7 +127,7 @@ struct Context {
     size_t ntt_table_bytes = 0;                   // bytes held by ntt_twiddles + ntt_scale_cache (budget: ntt.cu)
     std::map<unsigned, uint64_t> ntt_twiddle_use; // log2n -> last-use clock (LRU eviction together with the scale tables)
     // pointwise / scan workspaces (poly.cu)
-    DevBuf poly_tmp;
+    DevBuf poly_tmp, poly_stage;
     // Resident polynomials (resident.cu): device mirrors of caller-owned host arrays, keyed by host address, so that a
     // chain of calls on the same array (ifft -> commitment MSM -> coset FFT) crosses PCIe once.  Off unless enabled.
     struct Resident {

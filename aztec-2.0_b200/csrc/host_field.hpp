@@ -79,6 +79,43 @@ inline Fr from_u64(uint64_t v)
     return mul(a, r2);
 }
 inline Fr one() { return from_u64(1); }
+inline Fr zero()
+{
+    Fr r = { { 0, 0, 0, 0 } };
+    return r;
+}
+// canonical a + b and a - b (inputs any representative below 2^256 - r)
+inline Fr add(const Fr& a, const Fr& b)
+{
+    Fr x = reduce(a), y = reduce(b), r;
+    u128 c = 0;
+    for (int i = 0; i < 4; ++i) {
+        c += (u128)x.d[i] + y.d[i];
+        r.d[i] = (uint64_t)c;
+        c >>= 64;
+    }
+    while (geq_mod(r.d)) sub_mod(r.d); // x + y < 2r < 2^255: no carry out
+    return r;
+}
+inline Fr sub(const Fr& a, const Fr& b)
+{
+    Fr x = reduce(a), y = reduce(b), r;
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        u128 t = (u128)x.d[i] - y.d[i] - borrow;
+        r.d[i] = (uint64_t)t;
+        borrow = (uint64_t)(t >> 64) & 1;
+    }
+    if (borrow) {
+        u128 c = 0;
+        for (int i = 0; i < 4; ++i) {
+            c += (u128)r.d[i] + MOD[i];
+            r.d[i] = (uint64_t)c;
+            c >>= 64;
+        }
+    }
+    return r;
+}
 inline Fr pow(const Fr& a, const uint64_t e[4])
 {
     Fr acc = one();

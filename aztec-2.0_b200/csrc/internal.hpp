@@ -59,6 +59,8 @@ int resident_commit(Context* ctx, const void* host, size_t bytes, bool write_bac
 void resident_invalidate(Context* ctx, const void* host, size_t bytes);
 // Write every stale mirror overlapping [host, host + bytes) back to host memory (bytes == 0: all of them).
 int resident_flush(Context* ctx, const void* host, size_t bytes, cudaStream_t st);
+// true when a mirror containing the range holds data newer than host memory (a deferred write-back is pending)
+bool resident_is_ahead(Context* ctx, const void* host, size_t bytes);
 void resident_clear(Context* ctx);
 
 // ntt.cu

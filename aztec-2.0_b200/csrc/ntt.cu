@@ -22,6 +22,7 @@
 #include "ctx.cuh"
 #include "field.cuh"
 #include "internal.hpp"
+#include "poly.hpp"
 
 #include <algorithm>
 #include <cstdlib>
@@ -669,6 +670,27 @@ static int get_scale_table(Context* ctx, uint64_t count, const hf::Fr& start, co
     e.last_use = now;
     cache.push_back(e);
     return BBG_OK;
+}
+
+int ntt_root_table(Context* ctx, unsigned log_n, const void** table, cudaStream_t st)
+{
+    const fr* t = nullptr;
+    int rc = ensure_big_table(ctx, log_n, &t, st);
+    *table = t;
+    return rc;
+}
+int ntt_root_table_at_least(Context* ctx, unsigned log_n, const void** table, unsigned* stride_log, cudaStream_t st)
+{
+    for (auto& kv : ctx->ntt_twiddles) {
+        if (kv.first >= log_n) { // std::map: the smallest resident table that is large enough
+            ctx->ntt_twiddle_use[kv.first] = ++ctx->ntt_scale_clock;
+            *table = kv.second;
+            *stride_log = kv.first - log_n;
+            return BBG_OK;
+        }
+    }
+    *stride_log = 0;
+    return ntt_root_table(ctx, log_n, table, st);
 }
 
 // In-place (src == dst allowed) transform of 2^log_n elements on the device.

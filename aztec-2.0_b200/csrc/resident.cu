@@ -199,15 +199,15 @@ int resident_commit(Context* ctx, const void* host_v, size_t bytes, bool wb, cud
     return BBG_ERR_ARG;
 }
 
+// The mirrors keep their memory (the same arrays come back every proof); only their content is declared unknown:
+// the fingerprint is poisoned so the next use uploads, and a deferred write-back is abandoned.
 void resident_invalidate(Context* ctx, const void* host_v, size_t bytes)
 {
     const char* host = (const char*)host_v;
-    auto& tab = ctx->resident;
-    for (size_t i = tab.size(); i-- > 0;) {
-        Context::Resident& e = tab[i];
+    for (Context::Resident& e : ctx->resident) {
         if (bytes == 0 || (host < e.host + e.bytes && e.host < host + bytes)) {
-            cudaDeviceSynchronize();
-            drop(ctx, i);
+            for (uint32_t k = 0; k < e.n_samples; ++k) e.sample_val[k] = 0x9e3779b97f4a7c15ull * (k + 1) + e.sample_off[k];
+            e.host_stale = false;
         }
     }
 }
@@ -223,6 +223,15 @@ int resident_flush(Context* ctx, const void* host_v, size_t bytes, cudaStream_t 
         }
     }
     return BBG_OK;
+}
+
+bool resident_is_ahead(Context* ctx, const void* host_v, size_t bytes)
+{
+    const char* host = (const char*)host_v;
+    for (const Context::Resident& e : ctx->resident) {
+        if (host >= e.host && host + bytes <= e.host + e.bytes) return e.host_stale;
+    }
+    return false;
 }
 
 void resident_clear(Context* ctx)

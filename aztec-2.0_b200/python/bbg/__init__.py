@@ -35,7 +35,9 @@ EXPORTS = [
     "bbg_new_evaluation_domain", "bbg_delete_evaluation_domain", "bbg_ifft", "bbg_coset_fft_with_generator_shift",
     "bbg_domain_constants", "bbg_field_op", "bbg_g1_op",
     "bbg_pippenger_unsafe_batch", "bbg_pippenger_unsafe_batch_dev", "bbg_pippenger_batch",
-    "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
+    "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_ntt_ex", "bbg_wire_coset_fft", "bbg_turbo_quotient",
+    "bbg_permutation_quotient", "bbg_divide_by_pseudo_vanishing_polynomial", "bbg_compute_lagrange_polynomial_fft",
+    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
 ]
 
 
@@ -109,6 +111,16 @@ lib.bbg_pippenger_unsafe_batch_dev.argtypes = [_vp, _vp, _sz, _sz, _sz, _vp, _vp
 lib.bbg_pippenger_batch.argtypes = [_vp, _sz, _vp, _sz, _vp]
 lib.bbg_field_op_dev.argtypes = [_int, _int, _vp, _vp, _vp, _sz, _vp]
 lib.bbg_g1_normalize.argtypes = [_vp, _sz, _vp]
+lib.bbg_ntt_ex.argtypes = [_vp, _sz, _int, _sz, _vp, ctypes.c_uint]
+lib.bbg_wire_coset_fft.argtypes = [_vp, _vp, _sz, _sz, ctypes.c_uint]
+lib.bbg_turbo_quotient.argtypes = [_int, _vp, _sz, _vp, _vp, _vp, ctypes.c_uint]
+lib.bbg_permutation_quotient.argtypes = [_vp, _vp, ctypes.c_uint, _vp, _vp, _sz, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp, ctypes.c_uint]
+lib.bbg_divide_by_pseudo_vanishing_polynomial.argtypes = [_vp, _sz, _sz, ctypes.c_uint, ctypes.c_uint]
+lib.bbg_compute_lagrange_polynomial_fft.argtypes = [_vp, _sz, _sz]
+lib.bbg_permutation_grand_product.argtypes = [_vp, _vp, ctypes.c_uint, _sz, _vp, _vp, _vp, ctypes.c_uint]
+lib.bbg_evaluate.argtypes = [_vp, _sz, _vp, _vp]
+lib.bbg_compute_opening_polynomial.argtypes = [_vp, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint]
+lib.bbg_poly_write.argtypes = [_vp, _sz, _vp, _sz]
 lib.bbg_resident_mode.argtypes = [_int]
 lib.bbg_resident_invalidate.argtypes = [_vp, _sz]
 lib.bbg_resident_flush.argtypes = [_vp, _sz]
@@ -484,6 +496,97 @@ def field_op(field, op, a, b=None):
     out = np.zeros_like(a)
     _check(lib.bbg_field_op(field, op, a.ctypes.data, None if bb is None else bb.ctypes.data, out.ctypes.data, a.shape[0]))
     return out
+
+
+# ---- quotient-stage pointwise kernels and scans (include/bbg.h); numpy (host-pointer) flavour
+KEEP_ON_DEVICE, KEEP_IF_AHEAD = 1, 2
+NUM_POLYNOMIALS = 36
+WIDGET_TURBO_ARITHMETIC, WIDGET_TURBO_FIXED_BASE, WIDGET_TURBO_RANGE, WIDGET_TURBO_LOGIC = range(4)
+
+
+def _ptr_table(arrays, count):
+    """ctypes array of `count` host pointers; `arrays`: dict index -> numpy array, or a sequence"""
+    items = arrays.items() if isinstance(arrays, dict) else enumerate(arrays)
+    tab = [None] * count
+    for k, a in items:
+        tab[k] = a.ctypes.data
+    return (ctypes.c_void_p * count)(*tab)
+
+
+def _fr1(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint64).reshape(4))
+
+
+def turbo_quotient(kind, polys, n_large, alpha_base, alpha, quotient, flags=0):
+    """quotient (n_large, 4) += the gate identity of widget `kind`; polys: dict PolynomialIndex -> (n_large, 4) uint64"""
+    a0, a = _fr1(alpha_base), _fr1(alpha)
+    _check(lib.bbg_turbo_quotient(kind, ctypes.cast(_ptr_table(polys, NUM_POLYNOMIALS), _vp), n_large, a0.ctypes.data, a.ctypes.data,
+                                  quotient.ctypes.data, flags))
+    return quotient
+
+
+def permutation_quotient(wire_ffts, sigma_ffts, z_fft, lagrange_1, n_large, roots_cut, alpha_base, beta, gamma, delta, quotient, flags=0):
+    w = len(wire_ffts)
+    c = [_fr1(x) for x in (alpha_base, beta, gamma, delta)]
+    _check(lib.bbg_permutation_quotient(ctypes.cast(_ptr_table(wire_ffts, 4), _vp), ctypes.cast(_ptr_table(sigma_ffts, 4), _vp), w,
+                                        z_fft.ctypes.data, lagrange_1.ctypes.data, n_large, roots_cut, c[0].ctypes.data, c[1].ctypes.data,
+                                        c[2].ctypes.data, c[3].ctypes.data, quotient.ctypes.data, flags))
+    return quotient
+
+
+def divide_by_pseudo_vanishing_polynomial(evals, n_small, roots_cut=4, flags=0):
+    _check(lib.bbg_divide_by_pseudo_vanishing_polynomial(evals.ctypes.data, n_small, evals.size // 4, roots_cut, flags))
+    return evals
+
+
+def compute_lagrange_polynomial_fft(n_small, n_large):
+    out = np.zeros((n_large, 4), dtype=np.uint64)
+    _check(lib.bbg_compute_lagrange_polynomial_fft(out.ctypes.data, n_small, n_large))
+    return out
+
+
+def permutation_grand_product(wires, sigmas, n, beta, gamma, z=None, flags=0):
+    z = np.zeros((n, 4), dtype=np.uint64) if z is None else z
+    b, g = _fr1(beta), _fr1(gamma)
+    _check(lib.bbg_permutation_grand_product(ctypes.cast(_ptr_table(wires, 4), _vp), ctypes.cast(_ptr_table(sigmas, 4), _vp), len(wires), n,
+                                             b.ctypes.data, g.ctypes.data, z.ctypes.data, flags))
+    return z
+
+
+def evaluate(coeffs, z, n=None):
+    c = _np(coeffs, 4)
+    out = np.zeros(4, dtype=np.uint64)
+    zz = _fr1(z)
+    _check(lib.bbg_evaluate(c.ctypes.data, c.shape[0] if n is None else n, zz.ctypes.data, out.ctypes.data))
+    return out
+
+
+def compute_opening_polynomial(src, z, n_eval=None, n=None, dest=None, flags=0):
+    """(dest, F(z)); dest may be src itself (in place)"""
+    s = src if isinstance(src, np.ndarray) and src.dtype == np.uint64 and src.flags["C_CONTIGUOUS"] else _np(src, 4)
+    n_eval = s.size // 4 if n_eval is None else n_eval
+    n = n_eval if n is None else n
+    dest = np.zeros((n, 4), dtype=np.uint64) if dest is None else dest
+    f = np.zeros(4, dtype=np.uint64)
+    zz = _fr1(z)
+    _check(lib.bbg_compute_opening_polynomial(s.ctypes.data, dest.ctypes.data, zz.ctypes.data, n_eval, n, f.ctypes.data, flags))
+    return dest, f
+
+
+def wire_coset_fft(wire, wire_fft, n, ext=4, flags=0):
+    _check(lib.bbg_wire_coset_fft(wire.ctypes.data, wire_fft.ctypes.data, n, ext, flags))
+    return wire_fft
+
+
+def poly_write(host_array, elem_offset, values):
+    v = _np(values, 4)
+    _check(lib.bbg_poly_write(host_array.ctypes.data, elem_offset, v.ctypes.data, v.shape[0]))
+
+
+def ntt_ex(coeffs, kind, generator_size=0, constant=None, flags=0):
+    k = None if constant is None else _np(constant, 4)
+    _check(lib.bbg_ntt_ex(coeffs.ctypes.data, coeffs.size // 4, kind, generator_size, None if k is None else k.ctypes.data, flags))
+    return coeffs
 
 
 def field_op_dev(field, op, a, b=None, out=None, stream=None):

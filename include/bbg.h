@@ -170,6 +170,14 @@ int bbg_ntt_dist_layout(size_t n, int world, unsigned* in_pos, unsigned* out_pos
 int bbg_ntt_dist_dev(const void* d_src, void* d_dst, size_t n, int kind, size_t generator_size, const void* constant, int rank,
                      int world, int phase, void* stream);
 
+/* bbg_ntt with flags: BBG_KEEP_ON_DEVICE leaves the result in the array's device mirror (resident polynomials on;
+ * the host copy is stale until bbg_resident_flush) -- for transforms whose only consumers are further device steps */
+#define BBG_KEEP_ON_DEVICE 1u
+/* same, but only when the array's mirror is ALREADY ahead of host memory (an earlier step deferred its write-back):
+ * a generic entry point can then take part in a device-resident chain without ever hiding data from a host-side caller */
+#define BBG_KEEP_IF_AHEAD 2u
+int bbg_ntt_ex(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant, unsigned flags);
+
 /* coset_fft(coeffs, small_domain, large_domain, domain_extension) (polynomial_arithmetic.cpp:401-456):
  * coeffs holds ext*n elements, the first n are the input; output interleaved out[ext*i + k]. */
 int bbg_coset_fft_ext(void* coeffs, size_t n, size_t domain_extension);
@@ -183,6 +191,48 @@ int bbg_coset_fft_with_generator_shift(void* coeffs, const void* constant, void*
 /* evaluation_domain constants (bb/polynomials/evaluation_domain.cpp:57-76): root, root_inverse, domain,
  * domain_inverse, generator, generator_inverse -- 6 x 32 B, computed by the library's own host arithmetic */
 int bbg_domain_constants(size_t n, void* out6);
+
+/* ---- quotient-stage pointwise kernels and scans: the fr arithmetic that sits between the
+ * prover's NTTs and MSMs.  Host-pointer semantics like everything above; `flags` = 0 or BBG_KEEP_ON_DEVICE (outputs stay
+ * in their device mirror; needs resident polynomials).  All challenge / constant arguments are single fr elements. ---- */
+/* work_queue FFT item (bb/plonk/proof_system/prover/work_queue.hpp:260-270): wire_fft[0, ext*n + ext) = the ext*n-point coset
+ * FFT of the n coefficients in `wire` (zero padded, generator_size = n), followed by its first `ext` values again
+ * (polynomial::add_lagrange_base_coefficient x ext) */
+int bbg_wire_coset_fft(const void* wire, void* wire_fft, size_t n, size_t ext, unsigned flags);
+/* TransitionWidget::compute_quotient_contribution (bb/plonk/proof_system/widgets/transition_widgets/transition_widget.hpp:293-307)
+ * for the TurboPLONK gate kernels: quotient[i] += identity(i) over the n_large-point coset domain.
+ * polys: BBG_NUM_POLYNOMIALS pointers indexed like waffle::PolynomialIndex (types/polynomial_manifest.hpp:10-50) to the
+ * "_fft" arrays (n_large elements each; the ones the widget does not read may be null); alpha_base = the widget's first
+ * alpha power, alpha = the challenge. */
+#define BBG_NUM_POLYNOMIALS 36
+#define BBG_WIDGET_TURBO_ARITHMETIC 0   /* turbo_arithmetic_widget.hpp:17-143 */
+#define BBG_WIDGET_TURBO_FIXED_BASE 1   /* turbo_fixed_base_widget.hpp:17-160 */
+#define BBG_WIDGET_TURBO_RANGE 2        /* turbo_range_widget.hpp:30-161      */
+#define BBG_WIDGET_TURBO_LOGIC 3        /* turbo_logic_widget.hpp:17-183      */
+int bbg_turbo_quotient(int kind, const void* const* polys, size_t n_large, const void* alpha_base, const void* alpha, void* quotient,
+                       unsigned flags);
+/* ProverPermutationWidget<program_width, false>::compute_quotient_contribution (widgets/random_widgets/permutation_widget_impl.hpp:317-437):
+ * quotient[i] = alpha_base * (numerator - denominator) (assignment), identity permutation polynomials, coset generator 5 */
+int bbg_permutation_quotient(const void* const* wire_ffts, const void* const* sigma_ffts, unsigned program_width, const void* z_fft,
+                             const void* lagrange_1, size_t n_large, unsigned num_roots_cut, const void* alpha_base, const void* beta,
+                             const void* gamma, const void* public_input_delta, void* quotient, unsigned flags);
+/* polynomial_arithmetic::divide_by_pseudo_vanishing_polynomial(evaluations, src_domain, target_domain, k) (bb/polynomials/polynomial_arithmetic.cpp:628-725) */
+int bbg_divide_by_pseudo_vanishing_polynomial(void* evaluations, size_t n_small, size_t n_large, unsigned num_roots_cut, unsigned flags);
+/* polynomial_arithmetic::compute_lagrange_polynomial_fft(l_1, src_domain, target_domain) (:546-626) */
+int bbg_compute_lagrange_polynomial_fft(void* l_1_coefficients, size_t n_small, size_t n_large);
+/* the grand product of ProverPermutationWidget::compute_round_commitments (permutation_widget_impl.hpp:48-270): z[0] = 1,
+ * z[i] = prod_{j<i} prod_k (w_k[j] + gamma + beta k_k w^j) / (w_k[j] + gamma + beta sigma_k[j]), i < n; inputs in Lagrange base */
+int bbg_permutation_grand_product(const void* const* wires_lagrange, const void* const* sigmas_lagrange, unsigned program_width, size_t n,
+                                  const void* beta, const void* gamma, void* z, unsigned flags);
+/* polynomial_arithmetic::evaluate(coeffs, z, n) (:507-538): canonical fr result */
+int bbg_evaluate(const void* coeffs, size_t n, const void* z, void* result);
+/* KateCommitmentScheme::compute_opening_polynomial / compute_kate_opening_coefficients (commitment_scheme/kate_commitment_scheme.cpp:25-57,
+ * polynomial_arithmetic.cpp:727-751): dest[0, n) = coefficients of (F(X) - F(z)) / (X - z), F = src[0, n_eval); *f_at_z = F(z)
+ * (may be null); dest may equal src */
+int bbg_compute_opening_polynomial(const void* src, void* dest, const void* z, size_t n_eval, size_t n, void* f_at_z, unsigned flags);
+/* host_array[elem_offset, +count) = values, in host memory and in the array's device mirror (blinding scalars written
+ * between two device steps: prover.cpp:181-183, permutation_widget_impl.hpp:289-291) */
+int bbg_poly_write(void* host_array, size_t elem_offset, const void* values, size_t count);
 
 /* element-wise probe used by the L0 parity tests: out[i] = op(a[i], b[i]) on the device.
  * field: 0 fq, 1 fr.  op: 0 mul 1 add 2 sub 3 sqr 4 to_montgomery 5 from_montgomery 7 reduce_once 8 neg */

@@ -462,6 +462,39 @@ class Ref:
         return out
 
 
+def _ref_poly_methods():
+    """quotient-stage functions of the compiled reference (oracle/ref_shim.cpp), attached to Ref below"""
+    def divide_by_pseudo_vanishing_polynomial(self, evals, n_small, roots_cut=4):
+        c = aligned_copy(np.asarray(evals, dtype=np.uint64).reshape(-1, 4))
+        self.lib.ref_divide_by_pseudo_vanishing_polynomial(_p(c), self.domain(n_small), self.domain(c.shape[0]), ctypes.c_size_t(roots_cut))
+        return c
+
+    def compute_lagrange_polynomial_fft(self, n_small, n_large):
+        c = aligned_empty((n_large, 4))
+        self.lib.ref_compute_lagrange_polynomial_fft(_p(c), self.domain(n_small), self.domain(n_large))
+        return c
+
+    def compute_kate_opening_coefficients(self, src, z):
+        s_ = aligned_copy(np.asarray(src, dtype=np.uint64).reshape(-1, 4))
+        d = aligned_empty(s_.shape)
+        f = aligned_empty(4)
+        self.lib.ref_compute_kate_opening_coefficients(_p(s_), _p(d), _p(aligned_copy(z)), ctypes.c_size_t(s_.shape[0]), _p(f))
+        return d, f
+
+    def turbo_quotient(self, kind, polys, n_large, alpha_base, alpha, quotient):
+        """polys: dict PolynomialIndex -> (n_large, 4) array; returns the accumulated quotient (reference templates)"""
+        keep = {k: aligned_copy(np.asarray(v, dtype=np.uint64).reshape(-1, 4)) for k, v in polys.items()}
+        table = (ctypes.c_void_p * 36)(*[keep[k].ctypes.data if k in keep else None for k in range(36)])
+        q = aligned_copy(np.asarray(quotient, dtype=np.uint64).reshape(-1, 4))
+        self.lib.ref_turbo_quotient(kind, table, ctypes.c_size_t(n_large), _p(aligned_copy(alpha_base)), _p(aligned_copy(alpha)), _p(q))
+        return q
+    return (divide_by_pseudo_vanishing_polynomial, compute_lagrange_polynomial_fft, compute_kate_opening_coefficients, turbo_quotient)
+
+
+for _f in _ref_poly_methods():
+    setattr(Ref, _f.__name__, _f)
+
+
 def best_checker():
     """The reference itself when its .so travelled with the repo, else the plain-C restatement."""
     return Ref() if Ref.available() else Oracle()

@@ -29,6 +29,11 @@
 #include <polynomials/evaluation_domain.hpp>
 #include <polynomials/polynomial_arithmetic.hpp>
 #include <srs/io.hpp>
+// header-only gate kernels of the TurboPLONK widgets (templates over Field / Getters; nothing from plonk is linked)
+#include <plonk/proof_system/widgets/transition_widgets/turbo_arithmetic_widget.hpp>
+#include <plonk/proof_system/widgets/transition_widgets/turbo_fixed_base_widget.hpp>
+#include <plonk/proof_system/widgets/transition_widgets/turbo_logic_widget.hpp>
+#include <plonk/proof_system/widgets/transition_widgets/turbo_range_widget.hpp>
 
 #ifndef NO_MULTITHREADING
 #include <omp.h>
@@ -333,4 +338,76 @@ void ref_evaluate(const void* coeffs, const void* z, size_t n, void* out)
         polynomial_arithmetic::evaluate(reinterpret_cast<const fr*>(coeffs), *reinterpret_cast<const fr*>(z), n);
 }
 
+
+// ---- quotient-stage pointwise functions
+void ref_divide_by_pseudo_vanishing_polynomial(void* evals, void* small_dom, void* large_dom, size_t num_roots_cut)
+{
+    polynomial_arithmetic::divide_by_pseudo_vanishing_polynomial(reinterpret_cast<fr*>(evals), reinterpret_cast<ref_domain*>(small_dom)->d,
+                                                                 reinterpret_cast<ref_domain*>(large_dom)->d, num_roots_cut);
+}
+void ref_compute_lagrange_polynomial_fft(void* l1, void* small_dom, void* large_dom)
+{
+    polynomial_arithmetic::compute_lagrange_polynomial_fft(reinterpret_cast<fr*>(l1), reinterpret_cast<ref_domain*>(small_dom)->d,
+                                                           reinterpret_cast<ref_domain*>(large_dom)->d);
+}
+// fr compute_kate_opening_coefficients(src, dest, z, n) (polynomial_arithmetic.cpp:727-751); returns F(z) in f_out
+void ref_compute_kate_opening_coefficients(const void* src, void* dest, const void* z, size_t n, void* f_out)
+{
+    *reinterpret_cast<fr*>(f_out) = polynomial_arithmetic::compute_kate_opening_coefficients(
+        reinterpret_cast<const fr*>(src), reinterpret_cast<fr*>(dest), *reinterpret_cast<const fr*>(z), n);
+}
+
+} // extern "C"
+
+// The reference's gate kernels instantiated over raw arrays: exactly the three calls per evaluation point that
+// TransitionWidget::compute_quotient_contribution makes (transition_widget.hpp:293-307), with FFTGetter's indexing
+// ((index + 4) & block_mask for the shifted wires, :160-169).
+namespace {
+typedef waffle::widget::containers::poly_ptr_array<fr> raw_polys;
+struct RawGetters {
+    template <bool use_shifted_evaluation, waffle::PolynomialIndex id>
+    inline static const fr& get_polynomial(const raw_polys& polynomials, const size_t index = 0)
+    {
+        if constexpr (use_shifted_evaluation) {
+            return polynomials.coefficients[id][(index + 4) & polynomials.block_mask];
+        }
+        return polynomials.coefficients[id][index];
+    }
+};
+template <template <typename, typename, typename> typename KernelBase>
+void run_turbo_kernel(raw_polys& polynomials, size_t n_large, const fr& alpha_base, const fr& alpha, fr* quotient)
+{
+    typedef KernelBase<fr, RawGetters, raw_polys> Kernel;
+    constexpr size_t R = Kernel::num_independent_relations;
+    waffle::widget::containers::challenge_array<fr, R> challenges{};
+    challenges.elements[waffle::widget::ChallengeIndex::ALPHA] = alpha;
+    challenges.alpha_powers[0] = alpha_base;
+    for (size_t i = 1; i < R; ++i) challenges.alpha_powers[i] = challenges.alpha_powers[i - 1] * alpha;
+    for (size_t i = 0; i < n_large; ++i) {
+        waffle::widget::containers::coefficient_array<fr> linear_terms;
+        Kernel::compute_linear_terms(polynomials, challenges, linear_terms, i);
+        quotient[i] += Kernel::sum_linear_terms(polynomials, challenges, linear_terms, i);
+        Kernel::compute_non_linear_terms(polynomials, challenges, quotient[i], i);
+    }
+}
+} // namespace
+
+extern "C" {
+// kind: 0 arithmetic, 1 fixed base, 2 range, 3 logic; polys: MAX_NUM_POLYNOMIALS pointers indexed by waffle::PolynomialIndex
+void ref_turbo_quotient(int kind, const void* const* polys, size_t n_large, const void* alpha_base, const void* alpha, void* quotient)
+{
+    raw_polys p;
+    for (size_t k = 0; k < waffle::PolynomialIndex::MAX_NUM_POLYNOMIALS; ++k) {
+        p.coefficients[k] = const_cast<fr*>(reinterpret_cast<const fr*>(polys[k]));
+    }
+    p.block_mask = n_large - 1;
+    const fr a0 = *reinterpret_cast<const fr*>(alpha_base), a = *reinterpret_cast<const fr*>(alpha);
+    fr* q = reinterpret_cast<fr*>(quotient);
+    switch (kind) {
+    case 0: run_turbo_kernel<waffle::widget::TurboArithmeticKernel>(p, n_large, a0, a, q); break;
+    case 1: run_turbo_kernel<waffle::widget::TurboFixedBaseKernel>(p, n_large, a0, a, q); break;
+    case 2: run_turbo_kernel<waffle::widget::TurboRangeKernel>(p, n_large, a0, a, q); break;
+    default: run_turbo_kernel<waffle::widget::TurboLogicKernel>(p, n_large, a0, a, q); break;
+    }
+}
 } // extern "C"

@@ -1,9 +1,12 @@
 """End-to-end drop-in proof (BASELINE.json config #4): the reference's TurboPLONK join-split prover with its MSM / FFT
 entry points resolved to libbbg.so's CUDA kernels must emit the SAME 1 952 proof bytes as the all-CPU reference build.
 
-oracle/_ref/js_prover_cpu and js_prover_gpu are the same unmodified reference objects and the same harness
-(oracle/js_harness.cpp); in the second one the symbols aztec-2.0_b200/host/bbg_shim.cpp defines were weakened in the
-reference objects (oracle/Makefile `prover`).  Both use a deterministic numeric::random engine, so the blinding scalars
+oracle/_ref/js_prover_cpu, js_prover_gpu_l1 and js_prover_gpu are the same unmodified reference objects and the same
+harness (oracle/js_harness.cpp).  In js_prover_gpu_l1 the symbols aztec-2.0_b200/host/bbg_shim.cpp defines (MSM / NTT entry
+points) were weakened in the reference objects (oracle/Makefile `prover`); js_prover_gpu additionally links
+aztec-2.0_b200/host/bbg_prover_shim.cpp: work_queue::process_queue, the permutation widget (grand product and quotient
+contribution), the four Turbo gate widgets and divide_by_pseudo_vanishing_polynomial run on the device with the proof's
+polynomials resident in HBM.  Both use a deterministic numeric::random engine, so the blinding scalars
 and the noop transaction are identical and the Fiat-Shamir transcripts -- hence the proofs -- can be compared byte for
 byte.  Every proof is also checked by the reference verifier inside the harness.
 """
@@ -56,3 +59,19 @@ def test_join_split_proof_bytes_identical_on_gpu(golden_proof):
     assert c["gpu_kernel_launches"] == 0
     assert c["first_proof"] == g["first_proof"] and c["last_proof"] == g["last_proof"]
     print("join-split construct_proof: cpu %s  gpu %s" % (c["proofs"], g["proofs"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary,env", [
+    ("js_prover_gpu_l1", {}),                                   # round-1 flavour: only the L1 entry points replaced
+    ("js_prover_gpu", {"BBG_RESIDENT": "0"}),                  # device widgets, but every call uploads / downloads
+    ("js_prover_gpu", {"BBG_PROVER_SHIM": "0"}),               # reference queue logic over the device entry points
+    ("js_prover_gpu", {"BBG_STATS": "1", "BBG_SHIM_TRACE": "1"}),  # the full device-resident path, with accounting
+])
+def test_join_split_every_link_flavour_is_byte_identical(golden_proof, binary, env):
+    import bbg  # noqa: F401
+    g = _run(binary, 2, env=env)  # two proofs (the fixture's): mirrors kept from the first must not leak into the second
+    assert g["verified"] and g["proof_bytes"] == 1952
+    assert g["first_proof"] == golden_proof["first_proof"]
+    assert g["last_proof"] == golden_proof["last_proof"]
+    print("%s %s: keygen %.3f s, construct_proof %s" % (binary, env, g["keygen_s"], [p["construct_proof_s"] for p in g["proofs"]]))
