@@ -36,6 +36,7 @@
 #include <cooperative_groups.h>
 
 #include "g1.cuh"
+#include "g1_team.cuh"
 #include "internal.hpp"
 #include "inv.cuh"
 
@@ -744,25 +745,28 @@ __global__ void __launch_bounds__(128) k_msm_merge_rest(Slot* __restrict__ slots
 // and the last term is the SAME problem on the array T[1..] (weights 1, 2, ...), a factor ell0 smaller.  Level 0
 // (k_msm_segments<false>) is the throughput-bound sweep over all buckets; level 1 (k_msm_segments<true>) works on
 // T[1..] and finishes each segment with the double-and-add by its offset, which is now paid by B / (ell0 ell1)
-// workers instead of B / ell.  Everything here is latency bound (one lone-warp g1 addition is ~4.5 us), so the
+// workers instead of B / ell.  Everything here is latency bound (one g1 addition by a lone thread is ~6 us), so the
 // design minimises the serial chain: 2 ell0 + 2 ell1 + log2(B / ell0) additions/doublings, then one batched tree
-// sum over both levels and a 3-doubling Horner step in k_msm_finish.
+// sum over both levels and a short Horner step in k_msm_finish.
 // Worker (set, seg): items [seg*ell, min((seg+1)*ell, count)) of in + set*in_stride.  One add site: the loop
 // alternates run += x / acc += run.
-// (forcing 4 CTAs / SM here -- 128 registers, ~400 B of spills -- was measured slower: 0.62 vs 0.59 ms of reduce at 2^19 buckets)
+// Every worker below is a TEAM of four adjacent lanes (g1_team.cuh): the chains of this phase are far shorter than the
+// machine is wide, so each addition is spread over four lanes (4 multiply latencies instead of 14).
+static constexpr int SEG_THREADS = 128; // 32 teams per CTA
 template <bool OFFSET>
-__global__ void __launch_bounds__(128) k_msm_segments(const xyzz_t* __restrict__ in,
-                                                       uint32_t in_stride, // items between consecutive sets
-                                                       uint32_t count,     // items per set
-                                                       uint32_t ell,       // segment length
-                                                       uint32_t segs,      // segments per set = ceil(count / ell)
-                                                       uint32_t num_workers,
-                                                       xyzz_t* __restrict__ out_r,
-                                                       xyzz_t* __restrict__ out_t)
+__global__ void __launch_bounds__(SEG_THREADS) k_msm_segments(const xyzz_t* __restrict__ in,
+                                                               uint32_t in_stride, // items between consecutive sets
+                                                               uint32_t count,     // items per set
+                                                               uint32_t ell,       // segment length
+                                                               uint32_t segs,      // segments per set = ceil(count / ell)
+                                                               uint32_t num_workers,
+                                                               xyzz_t* __restrict__ out_r,
+                                                               xyzz_t* __restrict__ out_t)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const Team tm = team_of_lane();
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     if (t >= num_workers) {
-        return;
+        return; // team-uniform
     }
     const uint32_t set = t / segs, seg = t % segs;
     const xyzz_t* src = in + (size_t)set * in_stride;
@@ -779,7 +783,7 @@ __global__ void __launch_bounds__(128) k_msm_segments(const xyzz_t* __restrict__
             rhs = run;
         }
         xyzz_t lhs = xyzz_select(second, acc, run);
-        xyzz_add(lhs, rhs);
+        xyzz_add_team(tm, lhs, rhs);
         if (second) {
             acc = lhs;
         } else {
@@ -796,7 +800,7 @@ __global__ void __launch_bounds__(128) k_msm_segments(const xyzz_t* __restrict__
                 xyzz_t rhs;
                 bool do_add;
                 if (bit >= 0) {
-                    m = xyzz_dbl(m);
+                    xyzz_dbl_team(tm, m);
                     rhs = run;
                     do_add = (k >> bit) & 1;
                 } else {
@@ -804,13 +808,13 @@ __global__ void __launch_bounds__(128) k_msm_segments(const xyzz_t* __restrict__
                     do_add = true;
                 }
                 if (do_add) {
-                    xyzz_add(m, rhs);
+                    xyzz_add_team(tm, m, rhs);
                 }
             }
             acc = m;
         }
-        xyzz_store(out_r + t, acc);
-    } else {
+        if (tm.r == 0) xyzz_store(out_r + t, acc);
+    } else if (tm.r == 0) {
         xyzz_store(out_r + t, acc);
         xyzz_store(out_t + t, run);
     }
@@ -826,12 +830,17 @@ struct ReduceRows {
     uint32_t shift[REDUCE_MAX_LEVELS]; // log2(ell) of level l
 };
 
-// Sum of the XYZZ points of every row: grid (parts, rows); each CTA strides over its share and finishes with a
-// warp-shuffle tree + one shared-memory hop.  out[row * parts + part].  A CTA whose share is empty stores infinity.
+// lane-to-lane move of a whole point between TEAMS of one warp (delta in lanes, a multiple of 4)
+__device__ __forceinline__ xyzz_t xyzz_shfl_down_warp(const xyzz_t& p, int delta) { return xyzz_shfl_down(p, delta); }
+
+// Sum of the XYZZ points of every row: grid (parts, rows); the 64 teams of a CTA stride over its share, then a tree:
+// 3 steps across the 8 teams of each warp, one shared-memory hop, 3 steps across the warps.  out[row * parts + part].
 static constexpr int TREE_THREADS = 256;
+static constexpr int TREE_TEAMS = TREE_THREADS / 4;
 __global__ void __launch_bounds__(TREE_THREADS) k_msm_tree_sum(const xyzz_t* __restrict__ in, const ReduceRows rows, xyzz_t* __restrict__ out)
 {
     __shared__ xyzz_t sm[TREE_THREADS / 32];
+    const Team tm = team_of_lane();
     const uint32_t parts = gridDim.x, part = blockIdx.x, row = blockIdx.y;
     const uint32_t level = row / rows.S, set = row % rows.S;
     const uint32_t m = rows.m[level];
@@ -840,78 +849,82 @@ __global__ void __launch_bounds__(TREE_THREADS) k_msm_tree_sum(const xyzz_t* __r
     const uint32_t lo = part * per;
     const uint32_t hi = min(lo + per, m);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned team = threadIdx.x >> 2; // 0..63
     if (lo >= hi) { // uniform per CTA
         if (threadIdx.x == 0) xyzz_store(out + (size_t)row * parts + part, xyzz_infinity());
         return;
     }
-
     xyzz_t acc = xyzz_infinity();
-    const uint32_t iters = (per + TREE_THREADS - 1) / TREE_THREADS;
-    // steps [0, iters): strided loads; next 5: shuffle tree inside each warp; last 3: warp 0 folds the 8 warp sums
-    // (every addition is ~4.5 us of serial latency here, so the chain is kept as short as the shape allows)
-    for (uint32_t step = 0; step < iters + 8; ++step) {
+    const uint32_t iters = (per + TREE_TEAMS - 1) / TREE_TEAMS;
+    // steps [0, iters): strided loads; next 3: tree across the teams of a warp; last 3: warp 0 folds the 8 warp sums.
+    // The step count is uniform over the CTA, so the full-warp shuffles that move points between teams are legal.
+    for (uint32_t step = 0; step < iters + 6; ++step) {
         xyzz_t rhs = xyzz_infinity();
         if (step < iters) {
-            const uint32_t i = lo + step * TREE_THREADS + threadIdx.x;
+            const uint32_t i = lo + step * TREE_TEAMS + team;
             if (i < hi) rhs = xyzz_load(src + i);
         } else {
-            uint32_t delta = 16u >> (step - iters);
-            if (step >= iters + 5) {
-                if (step == iters + 5) {
+            uint32_t delta = 16u >> (step - iters); // lanes: 16, 8, 4
+            if (step >= iters + 3) {
+                if (step == iters + 3) {
                     if (lane == 0) sm[warp] = acc;
                     __syncthreads();
-                    acc = (warp == 0 && lane < TREE_THREADS / 32) ? sm[lane] : xyzz_infinity();
+                    acc = (warp == 0 && (lane >> 2) < TREE_THREADS / 32) ? sm[lane >> 2] : xyzz_infinity();
                 }
-                delta = 4u >> (step - iters - 5);
+                delta = 16u >> (step - iters - 3);
             }
-            rhs = xyzz_shfl_down(acc, (int)delta);
+            rhs = xyzz_shfl_down_warp(acc, (int)delta);
             if (lane + delta >= 32) rhs = xyzz_infinity();
         }
-        xyzz_add(acc, rhs);
+        xyzz_add_team(tm, acc, rhs);
     }
     if (threadIdx.x == 0) {
         xyzz_store(out + (size_t)row * parts + part, acc);
     }
 }
 
-// 6. per set: V = R_0 + ell_0 (R_1 + ell_1 (R_2 + ...)) (one thread per set), then
-//    result = sum_r 2^(c r) * V[r] (thread 0), XYZZ -> Jacobian.  level_sums[level * S + set].
-static constexpr int FINISH_THREADS = 256; // >= max number of bucket sets (windows): c >= 1 => W <= 255
+// 6. per set: V = R_0 + ell_0 (R_1 + ell_1 (R_2 + ...)) (one team per set), then
+//    result = sum_r 2^(c r) * V[r] (team 0), XYZZ -> Jacobian.  level_sums[level * S + set].
+static constexpr int FINISH_THREADS = 256; // 64 teams; more bucket sets than that are taken in turns
 __global__ void __launch_bounds__(FINISH_THREADS) k_msm_finish(const xyzz_t* __restrict__ level_sums, const ReduceRows rows, uint32_t c,
                                                                jac_t* __restrict__ out)
 {
-    __shared__ xyzz_t sm[FINISH_THREADS];
+    extern __shared__ xyzz_t sm_sets[]; // S entries
+    const Team tm = team_of_lane();
     const uint32_t S = rows.S;
-    if (threadIdx.x < S) {
-        // Horner from the deepest level; one add site and one doubling site
+    const uint32_t team = threadIdx.x >> 2;
+    for (uint32_t set = team; set < S; set += FINISH_THREADS / 4) {
+        // Horner from the deepest level
         xyzz_t v = xyzz_infinity();
         for (int level = (int)rows.levels - 1; level >= 0; --level) {
             for (uint32_t d = 0; d < rows.shift[level] && level != (int)rows.levels - 1; ++d) {
-                v = xyzz_dbl(v);
+                xyzz_dbl_team(tm, v);
             }
-            xyzz_t r = xyzz_load(level_sums + (size_t)level * S + threadIdx.x);
-            xyzz_add(v, r);
+            xyzz_t r = xyzz_load(level_sums + (size_t)level * S + set);
+            xyzz_add_team(tm, v, r);
         }
-        sm[threadIdx.x] = v;
+        if (tm.r == 0) sm_sets[set] = v;
     }
     __syncthreads();
-    if (threadIdx.x != 0) {
+    if (team != 0) {
         return;
     }
     xyzz_t acc = xyzz_infinity();
     for (int r = (int)S - 1; r >= 0; --r) {
         if (r != (int)S - 1) {
             for (uint32_t d = 0; d < c; ++d) {
-                acc = xyzz_dbl(acc);
+                xyzz_dbl_team(tm, acc);
             }
         }
-        xyzz_t s = sm[r];
-        xyzz_add(acc, s);
+        xyzz_t s = sm_sets[r];
+        xyzz_add_team(tm, acc, s);
     }
-    jac_t j = xyzz_to_jacobian(acc);
-    fe_store(&out->x, j.x);
-    fe_store(&out->y, j.y);
-    fe_store(&out->z, j.z);
+    if (tm.r == 0) {
+        jac_t j = xyzz_to_jacobian(acc);
+        fe_store(&out->x, j.x);
+        fe_store(&out->y, j.y);
+        fe_store(&out->z, j.z);
+    }
 }
 
 __global__ void k_set_infinity(jac_t* out)
@@ -923,16 +936,17 @@ __global__ void k_set_infinity(jac_t* out)
 }
 
 // sum of Jacobian elements (bb/ecc/curves/bn254/scalar_multiplication/c_bind.cpp:40-45 g1_sum);
-// one warp: lanes stride over the inputs, then a shuffle tree of g1 additions.
+// one warp = 8 teams: teams stride over the inputs, then a 3-step tree of cooperative g1 additions.
 __global__ void __launch_bounds__(32) k_g1_sum(const jac_t* __restrict__ in, uint32_t n, jac_t* __restrict__ out)
 {
-    const unsigned lane = threadIdx.x;
+    const Team tm = team_of_lane();
+    const unsigned lane = threadIdx.x, team = lane >> 2;
     xyzz_t acc = xyzz_infinity();
-    const uint32_t iters = (n + 31) / 32;
-    for (uint32_t step = 0; step < iters + 5; ++step) {
+    const uint32_t iters = (n + 7) / 8;
+    for (uint32_t step = 0; step < iters + 3; ++step) {
         xyzz_t rhs = xyzz_infinity();
         if (step < iters) {
-            const uint32_t i = step * 32 + lane;
+            const uint32_t i = step * 8 + team;
             if (i < n) {
                 jac_t j;
                 j.x = fe_load<FqParams>(&in[i].x);
@@ -945,7 +959,7 @@ __global__ void __launch_bounds__(32) k_g1_sum(const jac_t* __restrict__ in, uin
             rhs = xyzz_shfl_down(acc, d);
             if (lane + d >= 32) rhs = xyzz_infinity();
         }
-        xyzz_add(acc, rhs);
+        xyzz_add_team(tm, acc, rhs);
     }
     if (lane == 0) {
         jac_t j = xyzz_to_jacobian(acc);
@@ -1369,7 +1383,8 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
         const size_t total_segs = (size_t)segs0 + segs1;
         const unsigned levels = rows.levels;
         // parts: every first-stage CTA sums <= 2 entries per thread, the second stage <= 2 per thread as well
-        const uint32_t parts = std::min<uint32_t>(2 * TREE_THREADS, std::max<uint32_t>(1, segs0 / (2 * TREE_THREADS)));
+        // first stage: <= ~4 entries per team; second stage: parts / 64 per team
+        const uint32_t parts = std::min<uint32_t>(2 * TREE_TEAMS, std::max<uint32_t>(1, segs0 / (4 * TREE_TEAMS)));
         const size_t n_rows = (size_t)levels * S;
         // layout: R0 | V1 | T0 | per-part sums | per-row sums
         if ((rc = ws.reduce.reserve(((total_segs + segs0) * S + n_rows * parts + n_rows) * sizeof(xyzz_t)))) return rc;
@@ -1379,13 +1394,13 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
         xyzz_t* row_out = part_out + n_rows * parts;
         {
             const uint32_t workers = segs0 * (uint32_t)S;
-            k_msm_segments<false><<<div_up(workers, 128), 128, 0, st>>>(buckets, B, B, 1u << sh0, segs0, workers, r_all, t0);
+            k_msm_segments<false><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, st>>>(buckets, B, B, 1u << sh0, segs0, workers, r_all, t0);
             ctx->launches += 1;
         }
         if (count1) {
             const uint32_t workers = segs1 * (uint32_t)S;
-            k_msm_segments<true><<<div_up(workers, 128), 128, 0, st>>>(t0 + 1, segs0, count1, 1u << sh1, segs1, workers,
-                                                                       r_all + rows.off[1], nullptr);
+            k_msm_segments<true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, st>>>(t0 + 1, segs0, count1, 1u << sh1, segs1, workers,
+                                                                                                  r_all + rows.off[1], nullptr);
             ctx->launches += 1;
         }
         k_msm_tree_sum<<<dim3(parts, (unsigned)n_rows), TREE_THREADS, 0, st>>>(r_all, rows, part_out);
@@ -1402,7 +1417,7 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
             sums = row_out;
         }
         pr.mark(st, PH_MSM_COMBINE);
-        k_msm_finish<<<1, FINISH_THREADS, 0, st>>>(sums, rows, c, (jac_t*)d_out);
+        k_msm_finish<<<1, FINISH_THREADS, S * sizeof(xyzz_t), st>>>(sums, rows, c, (jac_t*)d_out);
         ctx->launches += 1;
     }
     pr.mark(st, -1);

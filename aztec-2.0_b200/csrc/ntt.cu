@@ -40,11 +40,31 @@ using fr = Fe<FrParams>;
 static constexpr int NTT_THREADS = 256;
 template <int LOGE> struct NttGeom {
     static constexpr int E = 1 << LOGE;                         // elements per thread = columns per tile
-    static constexpr int PAD = E + 1;                           // row pitch in 16-byte units (E columns + 1 pad)
+    // E = 4 uses an XOR-swizzled layout with no padding (sm_idx below); the others pad every row by one 16-byte unit
+    static constexpr int PAD = LOGE == 2 ? E : E + 1;           // row pitch in 16-byte units
     static constexpr int HALF_STRIDE = NTT_THREADS * PAD;       // 16-byte units between the two halves of an element
-    static constexpr int SMEM_BYTES = 2 * HALF_STRIDE * 16;     // E = 8: 73,728 B; E = 4: 40,960 B
+    static constexpr int SMEM_BYTES = 2 * HALF_STRIDE * 16;     // E = 8: 73,728 B; E = 4: 32,768 B; E = 2: 24,576 B
     static constexpr int MIN_CTAS = LOGE == 3 ? 2 : (LOGE == 2 ? 3 : 4);
 };
+
+// Shared-memory slot (in 16-byte units) of element (row, col) of tile `tile_local` (R rows per tile).
+// A 128-bit shared access is served a quarter-warp at a time: 8 lanes x 16 B = all 32 banks once if the 8 lanes hit 8
+// different 16-byte bank groups (slot mod 8).  With E = 4 columns a quarter-warp touches either (a) two rows that differ
+// in exactly ONE row bit x four columns (every radix-round exchange and the register load after the staging loop) or
+// (b) eight consecutive rows of one column (the transposing store of the last pass).  Row pitch E + 1 (round 1)
+// serves (b) but not (a): ncu showed 6.7-8 wavefronts per request where 4 is the floor.  The layout below serves both:
+//   two rows share a 128-byte line; bank group = parity(row) * 4 + (col ^ ((row >> 1) & 3))
+// (a): one differing bit flips the parity -> the two rows sit in different halves, columns stay distinct;
+// (b): (row >> 1) & 3 walks the four column slots and each slot's two rows (row, row + 1) have opposite parity.
+template <int LOGE> __device__ __forceinline__ uint32_t sm_idx(uint32_t tile_local, uint32_t R, uint32_t row, uint32_t col)
+{
+    if constexpr (LOGE == 2) {
+        const uint32_t line = (tile_local * R + row) >> 1; // R is even: a pair of rows never straddles two tiles
+        return (line << 3) | ((__popc(row) & 1u) << 2) | (col ^ ((row >> 1) & 3u));
+    } else {
+        return (tile_local * R + row) * (uint32_t)NttGeom<LOGE>::PAD + col;
+    }
+}
 static constexpr int NTT_MAX_PASSES = 4;
 static constexpr unsigned NTT_DEFAULT_LOGE = 2; // measured at 2^22: fft 0.892 ms with E = 4 vs 0.948 ms with E = 8 (BBG_NTT_LOGE=3)
 
@@ -225,12 +245,12 @@ template <> __device__ __forceinline__ void radix_round<3>(fr (&x)[8], uint32_t 
     radix8_round(x, g, w0, b_hi, lo, stage_tw); // hand-unrolled form: ptxas spills less with it than with the generic loops
 }
 
-template <int LOGE>
+// LAST is a template parameter so that each flavour only carries its own index maths in registers
+template <int LOGE, bool LAST>
 __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pass(const PassParams P)
 {
     extern __shared__ uint4 sm[];
     constexpr int E = NttGeom<LOGE>::E;
-    constexpr uint32_t NTT_PAD = NttGeom<LOGE>::PAD;
     const uint32_t half_stride = NttGeom<LOGE>::HALF_STRIDE;
 
     const uint32_t g = P.g;
@@ -244,14 +264,13 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
     const uint64_t num_tiles = (1ull << P.log_n) >> (g + LOGE); // local array
     const uint64_t tile = (uint64_t)blockIdx.x * tiles_per_cta + tile_local;
     const bool active = tile < num_tiles;
-    const uint32_t sm_base = tile_local * R * NTT_PAD; // this tile's rows inside the CTA's shared memory
     const uint32_t rows8 = R >> LOGE;
 
     // ---- tile coordinates
     uint64_t in_base = 0;     // address of (row 0, col 0)
     uint64_t rest0 = 0;       // non-last: first value of the low index; last: first o_1 of the tile
     uint64_t mid = 0;
-    if (!P.last) {
+    if constexpr (!LAST) {
         const uint64_t chunks = 1ull << (P.below - LOGE); // column chunks per hi value
         const uint64_t hi = tile / chunks;
         rest0 = (tile % chunks) << LOGE;
@@ -264,7 +283,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
 
     fr x[E];
     // ---- load (round-0 register layout: rows j * R/8 + q, column col)
-    if (!P.last) {
+    if constexpr (!LAST) {
         if (active) {
 #pragma unroll
             for (int j = 0; j < E; ++j) {
@@ -299,7 +318,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
                     a = ((uint64_t)src_rank << P.chunk_log) + (hi_idx << P.split_low) + low;
                 }
                 fr v = fe_load<FrParams>(P.src + a);
-                smem_store(sm, half_stride, sm_base + row * NTT_PAD + c, v);
+                smem_store(sm, half_stride, sm_idx<LOGE>(tile_local, R, row, c), v);
             }
         }
         __syncthreads();
@@ -307,7 +326,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
 #pragma unroll
             for (int j = 0; j < E; ++j) {
                 const uint32_t row = (uint32_t)j * rows8 + q;
-                x[j] = smem_load(sm, half_stride, sm_base + row * NTT_PAD + col);
+                x[j] = smem_load(sm, half_stride, sm_idx<LOGE>(tile_local, R, row, col));
             }
         }
     }
@@ -325,7 +344,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
                     const uint32_t row = (hi_part << (w0 + LOGE)) | ((uint32_t)j << w0) | lo_part;
-                    x[j] = smem_load(sm, half_stride, sm_base + row * NTT_PAD + col);
+                    x[j] = smem_load(sm, half_stride, sm_idx<LOGE>(tile_local, R, row, col));
                 }
             }
         }
@@ -343,7 +362,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
 #pragma unroll
             for (int j = 0; j < E; ++j) {
                 const uint32_t row = (hi_part << (w0 + LOGE)) | ((uint32_t)j << w0) | lo_part;
-                smem_store(sm, half_stride, sm_base + row * NTT_PAD + col, x[j]);
+                smem_store(sm, half_stride, sm_idx<LOGE>(tile_local, R, row, col), x[j]);
             }
         }
         first = false;
@@ -354,7 +373,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
     if (!active) {
         return;
     }
-    if (!P.last) {
+    if constexpr (!LAST) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const uint32_t rho = (q << LOGE) | (uint32_t)j;
@@ -798,9 +817,12 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
     }
 
     if (!ctx->ntt_attr_set) { // per context: a re-init on another device needs the attributes again
-        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<3>::SMEM_BYTES));
-        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
-        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<1>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<3>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<3>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<1>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<1>::SMEM_BYTES));
         ctx->ntt_attr_set = true;
     }
     // elements per thread (see NttGeom): 2^loge.  Measured on B200 (fft, ms; E = 2 / 4 / 8): 2^16 0.039 / 0.052 / 0.102 (the grid is
@@ -904,11 +926,14 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         const unsigned blocks = (unsigned)((num_tiles + tiles_per_cta - 1) / tiles_per_cta);
         pr.mark(st, PH_NTT_PASS0 + (int)p);
         if (loge == 1) {
-            k_ntt_pass<1><<<blocks, NTT_THREADS, NttGeom<1>::SMEM_BYTES, st>>>(pp);
+            if (last) k_ntt_pass<1, true><<<blocks, NTT_THREADS, NttGeom<1>::SMEM_BYTES, st>>>(pp);
+            else k_ntt_pass<1, false><<<blocks, NTT_THREADS, NttGeom<1>::SMEM_BYTES, st>>>(pp);
         } else if (loge == 2) {
-            k_ntt_pass<2><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
+            if (last) k_ntt_pass<2, true><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
+            else k_ntt_pass<2, false><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
         } else {
-            k_ntt_pass<3><<<blocks, NTT_THREADS, NttGeom<3>::SMEM_BYTES, st>>>(pp);
+            if (last) k_ntt_pass<3, true><<<blocks, NTT_THREADS, NttGeom<3>::SMEM_BYTES, st>>>(pp);
+            else k_ntt_pass<3, false><<<blocks, NTT_THREADS, NttGeom<3>::SMEM_BYTES, st>>>(pp);
         }
         ctx->launches += 1;
         above += gb[p];
