@@ -496,6 +496,20 @@ __global__ void __launch_bounds__(128) k_open_apply(const fr* __restrict__ f, ui
     }
 }
 
+// dest[i] = (base ? base[i] : 0) + sum_k polys[k][i] * scalars[k]   (the accumulation of KateCommitmentScheme::batch_open,
+// bb/plonk/proof_system/commitment_scheme/kate_commitment_scheme.cpp:213-222)
+__global__ void __launch_bounds__(128) k_linear_combination(const LinCombParams P)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    fr acc = P.base ? fe_load_nc<FrParams>(P.base + i) : fe_zero<FrParams>();
+#pragma unroll 1
+    for (uint32_t k = 0; k < P.count; ++k) {
+        acc = add(acc, mul(fe_load_nc<FrParams>(P.polys[k] + i), P.scalars[k]));
+    }
+    fe_store(P.dest + i, acc);
+}
+
 // dst[i] = i < n ? src[i] : 0 for i < total (copy_polynomial + zero padding, polynomial_arithmetic.cpp copy_polynomial)
 __global__ void __launch_bounds__(256) k_copy_pad(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16, size_t total16)
 {
@@ -768,6 +782,30 @@ int poly_opening_device(Context* ctx, const void* d_src, size_t n_in, size_t n_o
     k_open_top<<<1, OPEN_TOP_THREADS, 0, st>>>(tot, (uint32_t)m, dev_fr(hf::reduce(zc)));
     k_open_apply<<<div_up(m, 128), 128, 0, st>>>((const fr*)d_src, (uint32_t)n_in, (uint32_t)n_out, zd, tot, (fr*)d_dest, (fr*)d_f_at_z);
     ctx->launches += 3;
+    BBG_CUDA(cudaGetLastError());
+    return BBG_OK;
+}
+
+int poly_linear_combination_device(Context* ctx, void* d_dest, const void* d_base, const void* const* d_polys, const void* scalars, size_t count,
+                                   size_t n, cudaStream_t st)
+{
+    if (count > LINCOMB_MAX || n >= (1ull << 32)) {
+        set_last_error("linear_combination: at most " + std::to_string(LINCOMB_MAX) + " terms");
+        return BBG_ERR_ARG;
+    }
+    if (n == 0) return BBG_OK;
+    LinCombParams P;
+    memset(&P, 0, sizeof(P));
+    P.dest = (fr*)d_dest;
+    P.base = (const fr*)d_base;
+    P.n = (uint32_t)n;
+    P.count = (uint32_t)count;
+    for (size_t k = 0; k < count; ++k) {
+        P.polys[k] = (const fr*)d_polys[k];
+        P.scalars[k] = dev_fr(hf::reduce(hf::load((const char*)scalars + 32 * k)));
+    }
+    k_linear_combination<<<div_up(n, 128), 128, 0, st>>>(P);
+    ctx->launches += 1;
     BBG_CUDA(cudaGetLastError());
     return BBG_OK;
 }

@@ -56,6 +56,15 @@ struct GrandParams {
     Fe<FrParams> coset_gen[3];
 };
 
+static constexpr unsigned LINCOMB_MAX = 48;
+struct LinCombParams {
+    Fe<FrParams>* dest;
+    const Fe<FrParams>* base;
+    uint32_t n, count;
+    const Fe<FrParams>* polys[LINCOMB_MAX];
+    Fe<FrParams> scalars[LINCOMB_MAX];
+};
+
 // host-side argument bundles (device pointers)
 struct PermArgs {
     const void* d_wires[4];
@@ -84,6 +93,8 @@ int poly_lagrange_l1_device(Context* ctx, void* d_out, size_t n_small, size_t n_
 int poly_grand_product_device(Context* ctx, const GrandArgs& A, cudaStream_t st);
 int poly_evaluate_device(Context* ctx, const void* d_coeffs, size_t n, const hf::Fr& z, void* d_out, cudaStream_t st);
 int poly_opening_device(Context* ctx, const void* d_src, size_t n_in, size_t n_out, const hf::Fr& z, void* d_dest, void* d_f_at_z, cudaStream_t st);
+int poly_linear_combination_device(Context* ctx, void* d_dest, const void* d_base, const void* const* d_polys, const void* scalars, size_t count,
+                                   size_t n, cudaStream_t st);
 int poly_copy_pad_device(Context* ctx, const void* d_src, void* d_dst, size_t n, size_t total, cudaStream_t st);
 
 // ntt.cu: the cached table w_N^e, e in [0, N) (canonical values), N = 2^log_n; built on `st` on first use

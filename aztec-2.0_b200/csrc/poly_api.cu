@@ -370,6 +370,45 @@ int bbg_compute_opening_polynomial(const void* src, void* dest, const void* z, s
     return scope.tm.finish();
 }
 
+int bbg_linear_combination(void* dest, const void* base, const void* const* polys, const void* scalars, size_t count, size_t n, unsigned flags)
+{
+    GET_CTX();
+    StreamScope order(ctx, ctx->stream);
+    if (!dest || (count && (!polys || !scalars)) || count > LINCOMB_MAX) {
+        set_last_error("linear_combination: null argument or more than 48 terms");
+        return BBG_ERR_ARG;
+    }
+    Arg args[LINCOMB_MAX + 2];
+    for (size_t k = 0; k < count; ++k) {
+        args[k].host = polys[k];
+        args[k].bytes = n * 32;
+    }
+    Arg& b = args[LINCOMB_MAX];
+    b.host = base;
+    b.bytes = n * 32;
+    Arg& d = args[LINCOMB_MAX + 1];
+    d.host = dest;
+    d.bytes = n * 32;
+    d.need_data = false;
+    d.written = true;
+    // dest aliasing an input: keep its content
+    for (size_t k = 0; k < count; ++k) {
+        if (polys[k] == dest) d.need_data = true;
+    }
+    if (base == dest) d.need_data = true;
+    uint64_t h2d = 0, d2h = 0;
+    int rc;
+    if ((rc = bind(ctx, args, LINCOMB_MAX + 2, ctx->stream, &h2d))) return rc;
+    PolyScope scope(ctx);
+    const void* d_polys[LINCOMB_MAX];
+    for (size_t k = 0; k < count; ++k) d_polys[k] = args[k].d;
+    if ((rc = poly_linear_combination_device(ctx, d.d, base ? b.d : nullptr, d_polys, scalars, count, n, ctx->stream))) return rc;
+    scope.tm.stop();
+    if ((rc = finish(ctx, args, LINCOMB_MAX + 2, flags, ctx->stream, &d2h))) return rc;
+    scope.account(h2d, d2h);
+    return scope.tm.finish();
+}
+
 // work_queue FFT item (bb/plonk/proof_system/prover/work_queue.hpp:260-270): wire_fft[0, ext n + ext) = the ext n-point
 // coset FFT of the n wire coefficients, followed by its first `ext` values again
 int bbg_wire_coset_fft(const void* wire, void* wire_fft, size_t n, size_t ext, unsigned flags)

@@ -129,25 +129,31 @@ int resident_acquire(Context* ctx, const void* host_v, size_t bytes, bool need_d
             return BBG_OK;
         }
     }
-    // no mirror contains the range: retire mirrors that overlap it (a freed-and-reallocated neighbourhood)
+    // No mirror contains the range: mirrors that merely overlap it describe an array that no longer exists in that shape
+    // (freed and reallocated) and are retired.  The library NEVER writes into host memory on its own initiative: a
+    // pending write-back of such a mirror is abandoned -- its array is gone -- rather than scribbled over whatever lives
+    // there now.  Host memory is written only by a call that names the array (an entry point with that host pointer, or
+    // bbg_resident_flush), i.e. by a caller that vouches for it.
     for (size_t i = tab.size(); i-- > 0;) {
         Context::Resident& e = tab[i];
         if (host < e.host + e.bytes && e.host < host + bytes) {
-            if (e.host_stale && (rc = write_back(ctx, e, st))) return rc;
+            BBG_CUDA(cudaStreamSynchronize(st));
             drop(ctx, i);
         }
     }
-    // room: evict least-recently-used mirrors (writing deferred ones back first)
+    // room: evict least-recently-used mirrors; mirrors that are ahead of host memory hold the only copy and stay
     const size_t budget = resident_budget(ctx);
-    while (!tab.empty() && ctx->resident_bytes + bytes > budget) {
-        size_t victim = 0;
-        for (size_t i = 1; i < tab.size(); ++i) {
-            if (tab[i].last_use < tab[victim].last_use) victim = i;
+    while (ctx->resident_bytes + bytes > budget) {
+        size_t victim = tab.size();
+        for (size_t i = 0; i < tab.size(); ++i) {
+            if (tab[i].host_stale) continue;
+            if (victim == tab.size() || tab[i].last_use < tab[victim].last_use) victim = i;
         }
-        if (tab[victim].host_stale && (rc = write_back(ctx, tab[victim], st))) return rc;
+        if (victim == tab.size()) break; // nothing evictable: this array is simply not mirrored
         BBG_CUDA(cudaStreamSynchronize(st));
         drop(ctx, victim);
     }
+    if (ctx->resident_bytes + bytes > budget) return BBG_OK;
     if (bytes > budget) return BBG_OK; // too large to mirror: caller stages as before
     Context::Resident e;
     e.host = host;
@@ -254,8 +260,8 @@ int bbg_resident_mode(int enable)
     GET_CTX();
     if (enable < 0) return resident_enabled(ctx) ? 1 : 0;
     if (!enable && resident_enabled(ctx)) {
-        int rc = resident_flush(ctx, nullptr, 0, ctx->stream);
-        if (rc) return rc;
+        // mirrors are dropped, including ones whose write-back was deferred: flush first (bbg_resident_flush) if the host
+        // copies are still wanted -- the library does not write into arrays nobody named
         cudaDeviceSynchronize();
         resident_clear(ctx);
     }

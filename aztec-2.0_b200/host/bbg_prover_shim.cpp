@@ -12,6 +12,8 @@
 //   TransitionWidget<fr, {turbo,unrolled_turbo}_settings, Turbo{Arithmetic,FixedBase,Range,Logic}Kernel>::compute_quotient_contribution
 //                                                                                widgets/transition_widgets/transition_widget.hpp:293-307
 //   polynomial_arithmetic::divide_by_pseudo_vanishing_polynomial                 bb/polynomials/polynomial_arithmetic.cpp:628-725
+//   polynomial_arithmetic::evaluate                                              bb/polynomials/polynomial_arithmetic.cpp:507-538
+//   KateCommitmentScheme<{turbo,unrolled_turbo}_settings>::batch_open            commitment_scheme/kate_commitment_scheme.cpp:133-237
 //
 // What changes for a TurboPLONK proof (program width 4; every widget it uses is replaced here):
 //   * work items are submitted in batches: the four wire commitments / four quotient commitments of a round go to
@@ -37,7 +39,9 @@
 #include <plonk/proof_system/prover/work_queue.hpp>
 #undef private
 #include <common/throw_or_abort.hpp>
+#include <plonk/proof_system/commitment_scheme/kate_commitment_scheme.hpp>
 #include <plonk/proof_system/public_inputs/public_inputs.hpp>
+#include <plonk/proof_system/types/program_settings.hpp>
 #include <plonk/proof_system/types/prover_settings.hpp>
 #include <plonk/proof_system/widgets/random_widgets/permutation_widget.hpp>
 #include <plonk/proof_system/widgets/transition_widgets/turbo_arithmetic_widget.hpp>
@@ -290,6 +294,100 @@ void divide_by_pseudo_vanishing_polynomial(fr* coeffs, const evaluation_domain& 
 }
 } // namespace polynomial_arithmetic
 } // namespace barretenberg
+
+// ------------------------------------------------------------------------------------------------------------------
+// polynomial_arithmetic::evaluate: the ~30 opening evaluations of round 5 (kate_commitment_scheme.cpp:373-436) and
+// t(zeta) over 4n coefficients (prover.cpp:379) read polynomials whose mirrors are already on the device
+// ------------------------------------------------------------------------------------------------------------------
+namespace barretenberg {
+namespace polynomial_arithmetic {
+fr evaluate(const fr* coeffs, const fr& z, const size_t n)
+{
+    Trace trace("evaluate");
+    ensure_resident();
+    fr result;
+    check(bbg_evaluate(coeffs, n, &z, &result));
+    return result;
+}
+} // namespace polynomial_arithmetic
+} // namespace barretenberg
+
+// ------------------------------------------------------------------------------------------------------------------
+// KateCommitmentScheme::batch_open for program width 4.  The class is explicitly instantiated in the reference (extern
+// template in its header), so like process_queue the replacement is a free function carrying the member's mangled name;
+// the two std::shared_ptr arguments are passed by invisible reference (Itanium ABI), i.e. as pointers.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+template <typename settings>
+void batch_open_width4(const transcript::StandardTranscript& transcript, waffle::work_queue& queue, const std::shared_ptr<waffle::proving_key>& input_key,
+                       const std::shared_ptr<waffle::program_witness>& witness)
+{
+    static_assert(settings::program_width == 4, "the n + 1 coefficient of standard PLONK's t_high is not handled here");
+    Trace trace("batch_open");
+    using waffle::PolynomialSource;
+    std::vector<const void*> at_zeta, at_zeta_omega;
+    std::vector<fr> nu_zeta, nu_zeta_omega;
+    // the same tuples, in the same order, as kate_commitment_scheme.cpp:160-211
+    for (size_t i = 0; i < input_key->polynomial_manifest.size(); ++i) {
+        const auto& info = input_key->polynomial_manifest[i];
+        const std::string poly_label(info.polynomial_label);
+        fr* poly = nullptr;
+        switch (info.source) {
+        case PolynomialSource::WITNESS: poly = &witness->wires.at(poly_label)[0]; break;
+        case PolynomialSource::SELECTOR: poly = &input_key->constraint_selectors.at(poly_label)[0]; break;
+        case PolynomialSource::PERMUTATION: poly = &input_key->permutation_selectors.at(poly_label)[0]; break;
+        }
+        if (!info.is_linearised || !settings::use_linearisation) {
+            at_zeta.push_back(poly);
+            nu_zeta.push_back(transcript.get_challenge_field_element_from_map("nu", poly_label));
+        }
+        if (info.requires_shifted_evaluation) {
+            at_zeta_omega.push_back(poly);
+            nu_zeta_omega.push_back(transcript.get_challenge_field_element_from_map("nu", poly_label + "_omega"));
+        }
+    }
+    const fr zeta = transcript.get_challenge_field_element("z");
+    const size_t n = input_key->small_domain.size;
+    for (size_t i = 1; i < settings::program_width; ++i) {
+        const size_t offset = i * n;
+        at_zeta.push_back(&input_key->quotient_large[offset]);
+        nu_zeta.push_back(zeta.pow(static_cast<uint64_t>(offset)));
+    }
+    if constexpr (settings::use_linearisation) {
+        at_zeta.push_back(&input_key->linear_poly[0]);
+        nu_zeta.push_back(transcript.get_challenge_field_element_from_map("nu", "r"));
+    }
+    barretenberg::polynomial& opening_poly = input_key->opening_poly;
+    barretenberg::polynomial& shifted_opening_poly = input_key->shifted_opening_poly;
+    ensure_resident();
+    // both opening polynomials are only ever read again as MSM scalars (PI_Z, PI_Z_OMEGA): they stay on the device
+    const unsigned keep = bbg_resident_mode(-1) == 1 ? BBG_KEEP_ON_DEVICE : 0;
+    check(bbg_linear_combination(&opening_poly[0], &input_key->quotient_large[0], at_zeta.data(), nu_zeta.data(), at_zeta.size(), n, keep));
+    check(bbg_linear_combination(&shifted_opening_poly[0], nullptr, at_zeta_omega.data(), nu_zeta_omega.data(), at_zeta_omega.size(), n, keep));
+    const fr zeta_omega = zeta * input_key->small_domain.root;
+    check(bbg_compute_opening_polynomial(&opening_poly[0], &opening_poly[0], &zeta, n, n, nullptr, keep));
+    queue.add_to_queue({ waffle::work_queue::WorkType::SCALAR_MULTIPLICATION, &opening_poly[0], "PI_Z", fr(0), 0 });
+    check(bbg_compute_opening_polynomial(&shifted_opening_poly[0], &shifted_opening_poly[0], &zeta_omega, n, n, nullptr, keep));
+    queue.add_to_queue({ waffle::work_queue::WorkType::SCALAR_MULTIPLICATION, &shifted_opening_poly[0], "PI_Z_OMEGA", fr(0), 0 });
+}
+} // namespace
+
+extern "C" void bbg_shim_batch_open_unrolled_turbo(void* self, const transcript::StandardTranscript* transcript, waffle::work_queue* queue,
+                                                   std::shared_ptr<waffle::proving_key>* key, std::shared_ptr<waffle::program_witness>* witness)
+    asm("_ZN6waffle20KateCommitmentSchemeINS_23unrolled_turbo_settingsEE10batch_openERKN10transcript18StandardTranscriptERNS_10work_queueESt10shared_ptrINS_11proving_keyEES9_INS_15program_witnessEE");
+extern "C" void bbg_shim_batch_open_unrolled_turbo(void*, const transcript::StandardTranscript* transcript, waffle::work_queue* queue,
+                                                   std::shared_ptr<waffle::proving_key>* key, std::shared_ptr<waffle::program_witness>* witness)
+{
+    batch_open_width4<waffle::unrolled_turbo_settings>(*transcript, *queue, *key, *witness);
+}
+extern "C" void bbg_shim_batch_open_turbo(void* self, const transcript::StandardTranscript* transcript, waffle::work_queue* queue,
+                                          std::shared_ptr<waffle::proving_key>* key, std::shared_ptr<waffle::program_witness>* witness)
+    asm("_ZN6waffle20KateCommitmentSchemeINS_14turbo_settingsEE10batch_openERKN10transcript18StandardTranscriptERNS_10work_queueESt10shared_ptrINS_11proving_keyEES9_INS_15program_witnessEE");
+extern "C" void bbg_shim_batch_open_turbo(void*, const transcript::StandardTranscript* transcript, waffle::work_queue* queue,
+                                          std::shared_ptr<waffle::proving_key>* key, std::shared_ptr<waffle::program_witness>* witness)
+{
+    batch_open_width4<waffle::turbo_settings>(*transcript, *queue, *key, *witness);
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // widgets

@@ -37,7 +37,7 @@ EXPORTS = [
     "bbg_pippenger_unsafe_batch", "bbg_pippenger_unsafe_batch_dev", "bbg_pippenger_batch",
     "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_ntt_ex", "bbg_wire_coset_fft", "bbg_turbo_quotient",
     "bbg_permutation_quotient", "bbg_divide_by_pseudo_vanishing_polynomial", "bbg_compute_lagrange_polynomial_fft",
-    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
+    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
 ]
 
 
@@ -121,6 +121,7 @@ lib.bbg_permutation_grand_product.argtypes = [_vp, _vp, ctypes.c_uint, _sz, _vp,
 lib.bbg_evaluate.argtypes = [_vp, _sz, _vp, _vp]
 lib.bbg_compute_opening_polynomial.argtypes = [_vp, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint]
 lib.bbg_poly_write.argtypes = [_vp, _sz, _vp, _sz]
+lib.bbg_linear_combination.argtypes = [_vp, _vp, _vp, _vp, _sz, _sz, ctypes.c_uint]
 lib.bbg_resident_mode.argtypes = [_int]
 lib.bbg_resident_invalidate.argtypes = [_vp, _sz]
 lib.bbg_resident_flush.argtypes = [_vp, _sz]
@@ -571,6 +572,16 @@ def compute_opening_polynomial(src, z, n_eval=None, n=None, dest=None, flags=0):
     zz = _fr1(z)
     _check(lib.bbg_compute_opening_polynomial(s.ctypes.data, dest.ctypes.data, zz.ctypes.data, n_eval, n, f.ctypes.data, flags))
     return dest, f
+
+
+def linear_combination(polys, scalars, n, base=None, dest=None, flags=0):
+    """dest[i] = (base[i] or 0) + sum_k polys[k][i] * scalars[k]"""
+    dest = np.zeros((n, 4), dtype=np.uint64) if dest is None else dest
+    sc = _np(scalars, 4)
+    tab = (ctypes.c_void_p * max(len(polys), 1))(*[a.ctypes.data for a in polys])
+    _check(lib.bbg_linear_combination(dest.ctypes.data, None if base is None else base.ctypes.data, ctypes.cast(tab, _vp), sc.ctypes.data,
+                                      len(polys), n, flags))
+    return dest
 
 
 def wire_coset_fft(wire, wire_fft, n, ext=4, flags=0):

@@ -44,6 +44,38 @@ def ntt_sharded(bbg, local_in, n, kind, rank, world, generator_size=0, constant=
     return out
 
 
+def ntt_sharded_natural(bbg, block_in, n, kind, rank, world, generator_size=0, constant=None, group=None, phase_fn=None, layout=None):
+    """SURVEY.md 8e contract: rank r holds the NATURAL contiguous block x[r n/W, (r+1) n/W) and ends with the natural
+    block X[r n/W, (r+1) n/W).  The four-step core wants its input sliced by index bits [in_pos, in_pos + k) and leaves its
+    output sliced by bits [out_pos, ...); the two re-distributions are one all-to-all each:
+      in : element i of my block goes to rank bits(i); packed by (destination, index) the chunks received in rank order
+           ARE the destination's packed shard (global index order = source block major);
+      out: my packed output shard is ordered by global index, so the part belonging to rank q's block is the contiguous
+           chunk q; the receiver interleaves the chunks by the slicing bits.
+    Three all-to-alls in total (the sliced-layout entry point `ntt_sharded` needs one and remains the fast path when the
+    caller can produce / consume the sliced layout)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return ntt_sharded(bbg, block_in, n, kind, rank, world, generator_size, constant, group, phase_fn)
+    in_pos, out_pos = layout if layout is not None else bbg.ntt_dist_layout(n, world)
+    m = n // world
+    lb = m.bit_length() - 1  # bits of a block-local index; the slicing bits lie below the block bits (in_pos + k <= lb)
+    assert in_pos + (world.bit_length() - 1) <= lb and out_pos + (world.bit_length() - 1) <= lb
+    low = 1 << in_pos
+    # pack: (m / (low W), W, low, 4) -> destination-major
+    send = block_in.reshape(m // (low * world), world, low, 4).permute(1, 0, 2, 3).contiguous().reshape(m, 4)
+    shard_in = torch.empty_like(send)
+    dist.all_to_all_single(shard_in, send, group=group)
+    shard_out = ntt_sharded(bbg, shard_in, n, kind, rank, world, generator_size, constant, group, phase_fn)
+    recv = torch.empty_like(shard_out)
+    dist.all_to_all_single(recv, shard_out.contiguous(), group=group)  # chunk q of my shard = my part of rank q's block
+    low = 1 << out_pos
+    # unpack: chunk s holds the elements of my block whose slicing bits equal s, in index order
+    block_out = recv.reshape(world, m // (low * world), low, 4).permute(1, 0, 2, 3).contiguous().reshape(m, 4)
+    return block_out
+
+
 def simulate(bbg, x, kind, world, generator_size=0, constant=None):
     """All `world` ranks on one device. x: torch CUDA int64 (n, 4) natural order -> natural-order result."""
     import torch

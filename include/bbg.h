@@ -118,9 +118,12 @@ int bbg_pippenger_batch(const void* const* scalars, size_t count, const void* po
  * commitment MSM -> coset FFT of one wire polynomial crosses PCIe once.  Every mirror carries a fingerprint of the
  * host words it was made from (first / last elements + stratified samples) that is re-checked on each use, so an
  * array the caller rewrote in between is uploaded again.  Off by default (BBG_RESIDENT=1 or bbg_resident_mode(1)). */
-int bbg_resident_mode(int enable);                           /* 1 on, 0 off (flushes and frees), -1 query */
+int bbg_resident_mode(int enable);                           /* 1 on, 0 off (drops every mirror), -1 query */
 int bbg_resident_invalidate(const void* host, size_t bytes); /* forget mirrors overlapping the range (bytes 0: all) */
-int bbg_resident_flush(const void* host, size_t bytes);      /* write deferred mirrors back to host memory */
+/* Write mirrors that are ahead of host memory (BBG_KEEP_ON_DEVICE) back to the arrays overlapping [host, host+bytes)
+ * (bytes 0: all of them).  The ONLY way, besides an entry point called with that array, that the library writes host
+ * memory: the caller vouches that the arrays still exist.  Evictions and bbg_resident_mode(0) never write back. */
+int bbg_resident_flush(const void* host, size_t bytes);
 int bbg_resident_stats(uint64_t* out4);                      /* hits, misses, H2D bytes saved, bytes resident */
 
 /* bb/.../scalar_multiplication.hpp:139-148  pippenger(scalars, points, num_points, state, handle_edge_cases)
@@ -230,6 +233,9 @@ int bbg_evaluate(const void* coeffs, size_t n, const void* z, void* result);
  * polynomial_arithmetic.cpp:727-751): dest[0, n) = coefficients of (F(X) - F(z)) / (X - z), F = src[0, n_eval); *f_at_z = F(z)
  * (may be null); dest may equal src */
 int bbg_compute_opening_polynomial(const void* src, void* dest, const void* z, size_t n_eval, size_t n, void* f_at_z, unsigned flags);
+/* dest[i] = (base ? base[i] : 0) + sum_k polys[k][i] * scalars[k], i < n; count <= 48; scalars = count consecutive fr.
+ * The accumulation of the two opening polynomials in KateCommitmentScheme::batch_open (kate_commitment_scheme.cpp:213-222). */
+int bbg_linear_combination(void* dest, const void* base, const void* const* polys, const void* scalars, size_t count, size_t n, unsigned flags);
 /* host_array[elem_offset, +count) = values, in host memory and in the array's device mirror (blinding scalars written
  * between two device steps: prover.cpp:181-183, permutation_widget_impl.hpp:289-291) */
 int bbg_poly_write(void* host_array, size_t elem_offset, const void* values, size_t count);

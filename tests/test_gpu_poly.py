@@ -203,3 +203,23 @@ def test_poly_write_reaches_host_and_mirror(bbg, orc, srs_mini):
     want[n - 3:] = blind
     bbg.ifft(want)
     assert np.array_equal(canon(orc, z), canon(orc, want))
+
+
+@pytest.mark.parametrize("count,with_base", [(1, False), (5, True), (26, True), (48, False)])
+def test_linear_combination_vs_field_ops(bbg, orc, count, with_base):
+    """kate_commitment_scheme.cpp:213-222: opening_poly[i] = t[i] + sum_k poly_k[i] * nu_k"""
+    n = 1 << 10
+    polys = [inputs.fr_elements(500 + k, n, coarse_fraction=0.1) for k in range(count)]
+    sc = inputs.fr_elements(600, count)
+    base = inputs.fr_elements(601, n) if with_base else None
+    got = bbg.linear_combination(polys, sc, n, base=base)
+    want = base.copy() if with_base else np.zeros((n, 4), dtype=np.uint64)
+    for k in range(count):
+        term = orc.field_op(po.FR, po.OP_MUL, polys[k], np.repeat(sc[k:k + 1], n, axis=0))
+        want = orc.field_op(po.FR, po.OP_ADD, want, term)
+    assert np.array_equal(canon(orc, got), canon(orc, want))
+    # in place: dest is also the base
+    if with_base:
+        buf = base.copy()
+        bbg.linear_combination(polys, sc, n, base=buf, dest=buf)
+        assert np.array_equal(canon(orc, buf), canon(orc, want))

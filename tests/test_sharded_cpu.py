@@ -153,3 +153,42 @@ def test_ntt_four_step_plumbing_gloo_world2(tmp_path):
         shard = np.load(os.path.join(str(tmp_path), "ntt_r%d.npy" % r)).reshape(-1, 4)
         dist_ntt.insert_shard(out, shard, lg // 2 - 1, world, r)
     assert np.array_equal(out, exp)
+
+
+def _ntt_natural_worker(rank, world, port, lg, out_dir):
+    import torch
+    import torch.distributed as dist
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "aztec-2.0_b200", "python"), os.path.join(ROOT, "aztec-2.0_b200", "python", "bbg")):
+        sys.path.insert(0, p)
+    import inputs
+    import dist_ntt
+    from oracle import pyoracle as po
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    orc = po.Oracle()
+    n = 1 << lg
+    rb = world.bit_length() - 1
+    lg_a = lg_b = lg // 2
+    m = n // world
+    x = inputs.fr_elements(778, n)
+    block = torch.from_numpy(np.ascontiguousarray(x[rank * m:(rank + 1) * m]).view(np.int64))  # NATURAL contiguous block
+    out = dist_ntt.ntt_sharded_natural(None, block, n, po.NTT_FFT, rank, world, phase_fn=_cpu_phase(orc, po, lg_a, lg_b, rb),
+                                       layout=(lg_b - rb, lg_a - rb))
+    np.save(os.path.join(out_dir, "nat_r%d.npy" % rank), out.numpy().view(np.uint64))
+    dist.destroy_process_group()
+
+
+def test_ntt_natural_block_in_block_out_gloo_world2(tmp_path):
+    """input and output both block-distributed in natural order (ntt_sharded_natural = re-distribution
+    all-to-all + four-step core + re-distribution all-to-all), two CPU processes under gloo"""
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "aztec-2.0_b200", "python")):
+        sys.path.insert(0, p)
+    import inputs
+    from oracle import pyoracle as po
+    lg, world = 12, 2
+    n = 1 << lg
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_ntt_natural_worker, args=(world, port, lg, str(tmp_path)), nprocs=world, join=True)
+    orc = po.Oracle()
+    exp = np.array(orc.reduce(po.FR, orc.ntt(po.NTT_FFT, inputs.fr_elements(778, n))))
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), "nat_r%d.npy" % r)).reshape(-1, 4) for r in range(world)])
+    assert np.array_equal(got, exp)
