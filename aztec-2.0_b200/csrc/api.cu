@@ -426,13 +426,14 @@ void bbg_shutdown(void)
     g_ctx->ntt_scale_cache.clear();
     for (auto& ws : g_ctx->msm_ws) ws.release();
     DevBuf* bufs[] = { &g_ctx->msm_points, &g_ctx->ntt_data, &g_ctx->ntt_scratch, &g_ctx->ntt_pro, &g_ctx->ntt_epi, &g_ctx->ntt_small,
-                       &g_ctx->poly_tmp, &g_ctx->poly_stage };
+                       &g_ctx->poly_tmp, &g_ctx->poly_stage, &g_ctx->poly_out };
     for (auto* b : bufs) b->release();
     if (g_ctx->inv_fix_fq) cudaFree(g_ctx->inv_fix_fq);
     for (auto& e : g_ctx->prof.ev) {
         if (e) cudaEventDestroy(e);
     }
     g_staging.release();
+    if (g_ctx->pinned) cudaFreeHost(g_ctx->pinned);
     cudaEventDestroy(g_ctx->ev_a);
     cudaEventDestroy(g_ctx->ev_b);
     cudaEventDestroy(g_ctx->ev_fork);
@@ -743,6 +744,17 @@ static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, 
     }
     uint64_t h2d = 0;
     StatScope stat(STAT_MSM, ctx, 0, device_results ? 0 : 96 * count);
+    // Host results go through a pinned staging buffer: a device-to-host copy into pageable memory blocks the calling
+    // thread until the MSM before it has finished, which would serialise the batch on the host (the next MSM would
+    // not even be queued yet) and throw the overlap away.
+    if (!device_results && count * 96 > ctx->pinned_cap) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+        const size_t cap = std::max<size_t>(count * 96, 4096);
+        BBG_CUDA(cudaHostAlloc(&ctx->pinned, cap, cudaHostAllocDefault));
+        ctx->pinned_cap = cap;
+    }
     for (size_t i = 0; i < count; ++i) {
         MsmWorkspace& ws = ctx->msm_ws[i & 1];
         cudaStream_t s = st[i & 1];
@@ -767,7 +779,7 @@ static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, 
             d_out = ws.result.p;
         }
         if ((rc = msm_device(ctx, ws, d_sc, range, o->d_points, 1, o->lv, from, d_out, s))) return rc;
-        if (!device_results) BBG_CUDA(cudaMemcpyAsync((char*)results + i * 96, d_out, 96, cudaMemcpyDeviceToHost, s));
+        if (!device_results) BBG_CUDA(cudaMemcpyAsync((char*)ctx->pinned + i * 96, d_out, 96, cudaMemcpyDeviceToHost, s));
     }
     if (stat.row) stat.row->bytes_h2d += h2d;
     stat.h2d = h2d;
@@ -775,7 +787,10 @@ static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, 
         BBG_CUDA(cudaEventRecord(ctx->ev_join, st[1]));
         BBG_CUDA(cudaStreamWaitEvent(st0, ctx->ev_join, 0));
     }
-    if (!device_results) BBG_CUDA(cudaStreamSynchronize(st0));
+    if (!device_results) {
+        BBG_CUDA(cudaStreamSynchronize(st0));
+        memcpy(results, ctx->pinned, count * 96);
+    }
     return BBG_OK;
 }
 

@@ -126,8 +126,11 @@ struct Context {
     bool ntt_attr_set = false;                    // cudaFuncSetAttribute done for this context's device
     size_t ntt_table_bytes = 0;                   // bytes held by ntt_twiddles + ntt_scale_cache (budget: ntt.cu)
     std::map<unsigned, uint64_t> ntt_twiddle_use; // log2n -> last-use clock (LRU eviction together with the scale tables)
+    // small pinned staging buffer for results of batched calls
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
     // pointwise / scan workspaces (poly.cu)
-    DevBuf poly_tmp, poly_stage;
+    DevBuf poly_tmp, poly_stage, poly_out;
     // Resident polynomials (resident.cu): device mirrors of caller-owned host arrays, keyed by host address, so that a
     // chain of calls on the same array (ifft -> commitment MSM -> coset FFT) crosses PCIe once.  Off unless enabled.
     struct Resident {

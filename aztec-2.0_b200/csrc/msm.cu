@@ -33,16 +33,12 @@
 // traffic is ~(32 + 68*W) B per point.  No kernel calls a non-inlined device function (see g1.cuh).
 #include <algorithm>
 
-#include <cooperative_groups.h>
-
 #include "g1.cuh"
 #include "g1_team.cuh"
 #include "internal.hpp"
 #include "inv.cuh"
 
 namespace bbg {
-
-namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------------
 // 1/3. digits: histogram (SCATTER = false) or counting-sort scatter (SCATTER = true)
@@ -706,28 +702,27 @@ __global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
     merge_worker(in, n_in, workers, u, buckets, out, pending_out);
 }
 
-// levels 1..: ONE cooperative launch loops over the remaining levels with a grid barrier in between and stops at the
-// first level that has nothing open -- for uniform scalars that is immediately (a bucket would have to span more than
-// MERGE_K / 2 chunks), so the round-1 chain of up to 13 early-exit launches (~3 us each) is gone; when every scalar is
-// equal the loop still runs the full log-depth merge.
-__global__ void __launch_bounds__(128) k_msm_merge_rest(Slot* __restrict__ slots, uint32_t n_in, uint32_t* __restrict__ pending,
-                                                         xyzz_t* __restrict__ buckets)
+// Levels 0-2 are ordinary grid-wide launches of k_msm_merge (each exits at once when the level before left nothing
+// open); whatever is still open after them -- only when a handful of buckets hold most of the digits, e.g. all scalars
+// equal -- is finished by ONE single-CTA launch that loops over the remaining levels with a block barrier in between
+// (level 3 has at most num_chunks / 256 workers).  Round 1 launched up to 14 levels one by one.
+static constexpr int MERGE_GRID_LEVELS = 3;
+static constexpr int MERGE_REST_THREADS = 512;
+__global__ void __launch_bounds__(MERGE_REST_THREADS) k_msm_merge_rest(Slot* __restrict__ slots, uint32_t n_in, uint32_t first_level,
+                                                                        uint32_t* __restrict__ pending, xyzz_t* __restrict__ buckets)
 {
-    cg::grid_group grid = cg::this_grid();
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nthreads = gridDim.x * blockDim.x;
     Slot* in = slots;
-    for (uint32_t level = 1; level < 15; ++level) {
+    for (uint32_t level = first_level; level < 15; ++level) {
         if (*(volatile uint32_t*)(pending + level) == 0) {
             break; // uniform: every thread reads the same counter after the barrier
         }
         const uint32_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
         Slot* out = in + n_in;
-        for (uint32_t u = tid; u < workers; u += nthreads) {
+        for (uint32_t u = threadIdx.x; u < workers; u += MERGE_REST_THREADS) {
             merge_worker(in, n_in, workers, u, buckets, out, pending + level + 1);
         }
         __threadfence();
-        grid.sync();
+        __syncthreads();
         if (workers == 1) {
             break;
         }
@@ -753,8 +748,11 @@ __global__ void __launch_bounds__(128) k_msm_merge_rest(Slot* __restrict__ slots
 // Every worker below is a TEAM of four adjacent lanes (g1_team.cuh): the chains of this phase are far shorter than the
 // machine is wide, so each addition is spread over four lanes (4 multiply latencies instead of 14).
 static constexpr int SEG_THREADS = 128; // 32 teams per CTA
-template <bool OFFSET>
-__global__ void __launch_bounds__(SEG_THREADS) k_msm_segments(const xyzz_t* __restrict__ in,
+// TEAM: a worker is a team of four lanes (cooperative additions: shortest chain) -- the right shape while there are
+// fewer workers than the GPU has lanes.  !TEAM: one thread per worker (plain additions: ~14 % fewer multiplies, no
+// shuffles) -- the right shape for level 0 of a large bucket set, which is throughput bound.
+template <bool OFFSET, bool TEAM>
+__global__ void __launch_bounds__(SEG_THREADS, TEAM ? 1 : 3) k_msm_segments(const xyzz_t* __restrict__ in,
                                                                uint32_t in_stride, // items between consecutive sets
                                                                uint32_t count,     // items per set
                                                                uint32_t ell,       // segment length
@@ -764,10 +762,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k_msm_segments(const xyzz_t* __re
                                                                xyzz_t* __restrict__ out_t)
 {
     const Team tm = team_of_lane();
-    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = TEAM ? gtid >> 2 : gtid;
     if (t >= num_workers) {
         return; // team-uniform
     }
+    const bool writer = !TEAM || tm.r == 0;
     const uint32_t set = t / segs, seg = t % segs;
     const xyzz_t* src = in + (size_t)set * in_stride;
     const uint32_t first = seg * ell;
@@ -783,7 +783,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k_msm_segments(const xyzz_t* __re
             rhs = run;
         }
         xyzz_t lhs = xyzz_select(second, acc, run);
-        xyzz_add_team(tm, lhs, rhs);
+        if (TEAM) {
+            xyzz_add_team(tm, lhs, rhs);
+        } else {
+            xyzz_add(lhs, rhs);
+        }
         if (second) {
             acc = lhs;
         } else {
@@ -800,7 +804,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k_msm_segments(const xyzz_t* __re
                 xyzz_t rhs;
                 bool do_add;
                 if (bit >= 0) {
-                    xyzz_dbl_team(tm, m);
+                    if (TEAM) {
+                        xyzz_dbl_team(tm, m);
+                    } else {
+                        m = xyzz_dbl(m);
+                    }
                     rhs = run;
                     do_add = (k >> bit) & 1;
                 } else {
@@ -808,13 +816,17 @@ __global__ void __launch_bounds__(SEG_THREADS) k_msm_segments(const xyzz_t* __re
                     do_add = true;
                 }
                 if (do_add) {
-                    xyzz_add_team(tm, m, rhs);
+                    if (TEAM) {
+                        xyzz_add_team(tm, m, rhs);
+                    } else {
+                        xyzz_add(m, rhs);
+                    }
                 }
             }
             acc = m;
         }
-        if (tm.r == 0) xyzz_store(out_r + t, acc);
-    } else if (tm.r == 0) {
+        if (writer) xyzz_store(out_r + t, acc);
+    } else if (writer) {
         xyzz_store(out_r + t, acc);
         xyzz_store(out_t + t, run);
     }
@@ -1340,33 +1352,40 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
     ctx->launches += 1;
     pr.mark(st, PH_MSM_FIXUP);
     {
-        const size_t n_in = 2 * num_chunks;
-        const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
-        Slot* out = slots + n_in;
-        k_msm_merge<<<div_up(workers, 128), 128, 0, st>>>(slots, (uint32_t)n_in, (uint32_t)workers, pending, buckets, out, pending + 1);
-        ctx->launches += 1;
-        if (workers > 1) {
-            static int ctas_per_sm = 0; // occupancy of the cooperative kernel (all of its CTAs must be co-resident)
-            if (ctas_per_sm == 0) {
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_msm_merge_rest, 128, 0) != cudaSuccess || ctas_per_sm < 1) {
-                    ctas_per_sm = 1;
-                }
+        size_t n_in = 2 * num_chunks;
+        Slot* in = slots;
+        unsigned level = 0;
+        while (true) {
+            const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
+            Slot* out = in + n_in;
+            if (level < MERGE_GRID_LEVELS) {
+                k_msm_merge<<<div_up(workers, 128), 128, 0, st>>>(in, (uint32_t)n_in, (uint32_t)workers, pending + level, buckets, out,
+                                                                 pending + level + 1);
+                ctx->launches += 1;
+            } else {
+                k_msm_merge_rest<<<1, MERGE_REST_THREADS, 0, st>>>(in, (uint32_t)n_in, level, pending, buckets);
+                ctx->launches += 1;
+                break;
             }
-            const uint32_t workers1 = (uint32_t)((2 * workers - 1 + MERGE_K - 1) / MERGE_K);
-            const unsigned grid = std::max(1u, std::min<unsigned>(div_up(workers1, 128), (unsigned)(ctx->num_sms * ctas_per_sm)));
-            Slot* lvl1_in = out;
-            uint32_t lvl1_n = (uint32_t)(2 * workers);
-            void* args[] = { (void*)&lvl1_in, (void*)&lvl1_n, (void*)&pending, (void*)&buckets };
-            BBG_CUDA(cudaLaunchCooperativeKernel((const void*)k_msm_merge_rest, dim3(grid), dim3(128), args, 0, st));
-            ctx->launches += 1;
+            ++level;
+            if (workers == 1) break;
+            in = out;
+            n_in = 2 * workers;
         }
     }
 
     // bucket reduction (see the comment above k_msm_segments)
     pr.mark(st, PH_MSM_REDUCE);
     {
-        const unsigned sh0 = std::min(6u, env_uint("BBG_MSM_ELL0_LOG2", B >= (1u << 18) ? 4u : 2u));
-        const unsigned sh1 = std::min(6u, env_uint("BBG_MSM_ELL1_LOG2", 2u));
+        // Level 0 sweeps all B buckets (2 additions each, throughput bound once B is large): short segments there give
+        // many workers; level 1 sweeps the B / ell0 segment sums with cooperative teams.
+        // Measured on B200, 2^19 buckets (ms of bucket reduction; round 1's shape ell0 = 16, ell1 = 4 with plain additions: 0.65):
+        // teams at both levels 16/4: 0.65, 4/16: 0.77; plain level 0 + team level 1: 4/8 0.61, 4/16 0.53, 4/32 0.58,
+        // 8/8 0.51, 8/16 0.53, 2/16 0.73.  Small bucket sets (2^15 buckets, c = 16): teams at both levels, 4/4: 0.18 (0.34).
+        const bool big = B >= (1u << 18);
+        const unsigned sh0 = std::min(6u, env_uint("BBG_MSM_ELL0_LOG2", big ? 3u : 2u));
+        const unsigned sh1 = std::min(6u, env_uint("BBG_MSM_ELL1_LOG2", big ? 3u : 2u));
+        const bool team0 = env_uint("BBG_MSM_SEG0_TEAM", ((size_t)S * (B >> sh0)) < (1u << 16) ? 1u : 0u) != 0;
         ReduceRows rows;
         memset(&rows, 0, sizeof(rows));
         rows.S = (uint32_t)S;
@@ -1394,13 +1413,17 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
         xyzz_t* row_out = part_out + n_rows * parts;
         {
             const uint32_t workers = segs0 * (uint32_t)S;
-            k_msm_segments<false><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, st>>>(buckets, B, B, 1u << sh0, segs0, workers, r_all, t0);
+            if (team0) {
+                k_msm_segments<false, true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, st>>>(buckets, B, B, 1u << sh0, segs0, workers, r_all, t0);
+            } else {
+                k_msm_segments<false, false><<<div_up(workers, SEG_THREADS), SEG_THREADS, 0, st>>>(buckets, B, B, 1u << sh0, segs0, workers, r_all, t0);
+            }
             ctx->launches += 1;
         }
         if (count1) {
             const uint32_t workers = segs1 * (uint32_t)S;
-            k_msm_segments<true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, st>>>(t0 + 1, segs0, count1, 1u << sh1, segs1, workers,
-                                                                                                  r_all + rows.off[1], nullptr);
+            k_msm_segments<true, true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, st>>>(t0 + 1, segs0, count1, 1u << sh1, segs1, workers,
+                                                                                                        r_all + rows.off[1], nullptr);
             ctx->launches += 1;
         }
         k_msm_tree_sum<<<dim3(parts, (unsigned)n_rows), TREE_THREADS, 0, st>>>(r_all, rows, part_out);

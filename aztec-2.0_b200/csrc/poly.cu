@@ -377,9 +377,14 @@ __global__ void __launch_bounds__(128) k_perm_finish(const fr* __restrict__ num,
 // ------------------------------------------------------------------------------------------------
 static constexpr int EVAL_CHUNK = 16;
 static constexpr int EVAL_THREADS = 256;
-__global__ void __launch_bounds__(EVAL_THREADS) k_eval_partial(const fr* __restrict__ c, uint32_t n, fr z, fr z_chunk /* z^EVAL_CHUNK */, fr* __restrict__ partial)
+// blockIdx.y selects the polynomial (batched evaluation: the ~30 opening evaluations of round 5 in one launch)
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_partial(const EvalBatchParams P, fr* __restrict__ partial)
 {
     __shared__ fr sm[EVAL_THREADS];
+    const uint32_t y = blockIdx.y;
+    const fr* c = P.coeffs[y];
+    const uint32_t n = P.n[y];
+    const fr z = P.z[y];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i0 = t * EVAL_CHUNK;
     fr acc = fe_zero<FrParams>();
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_partial(const fr* __restr
             acc = mul(acc, z);
             if (i0 + j < n) acc = add(acc, fe_load_nc<FrParams>(c + i0 + j));
         }
-        acc = mul(acc, fe_pow(z_chunk, (uint64_t)t));
+        acc = mul(acc, fe_pow(P.z_chunk[y], (uint64_t)t));
     }
     sm[threadIdx.x] = acc;
     __syncthreads();
@@ -398,11 +403,12 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_partial(const fr* __restr
         if (threadIdx.x < d) sm[threadIdx.x] = add(sm[threadIdx.x], sm[threadIdx.x + d]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) fe_store(partial + blockIdx.x, sm[0]);
+    if (threadIdx.x == 0) fe_store(partial + (size_t)y * gridDim.x + blockIdx.x, sm[0]);
 }
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_final(const fr* __restrict__ partial, uint32_t m, fr* __restrict__ out)
 {
     __shared__ fr sm[EVAL_THREADS];
+    partial += (size_t)blockIdx.x * m;
     fr acc = fe_zero<FrParams>();
     for (uint32_t i = threadIdx.x; i < m; i += EVAL_THREADS) acc = add(acc, fe_load<FrParams>(partial + i));
     sm[threadIdx.x] = acc;
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_final(const fr* __restric
         if (threadIdx.x < d) sm[threadIdx.x] = add(sm[threadIdx.x], sm[threadIdx.x + d]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) fe_store(out, fe_reduce_once(sm[0]));
+    if (threadIdx.x == 0) fe_store(out + blockIdx.x, fe_reduce_once(sm[0]));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -744,24 +750,46 @@ int poly_grand_product_device(Context* ctx, const GrandArgs& A, cudaStream_t st)
     return BBG_OK;
 }
 
-int poly_evaluate_device(Context* ctx, const void* d_coeffs, size_t n, const hf::Fr& z, void* d_out, cudaStream_t st)
+// out[k] = sum_i coeffs_k[i] z_k^i, k < count <= EVAL_BATCH_MAX; one launch for the whole batch
+int poly_evaluate_batch_device(Context* ctx, const void* const* d_coeffs, const size_t* n, const void* zs, size_t count, void* d_out, cudaStream_t st)
 {
-    if (n >= (1ull << 32)) {
-        set_last_error("evaluate: too many coefficients");
+    if (count == 0) return BBG_OK;
+    if (count > EVAL_BATCH_MAX) {
+        set_last_error("evaluate: at most " + std::to_string(EVAL_BATCH_MAX) + " polynomials per batch");
         return BBG_ERR_ARG;
     }
-    const size_t threads = (n + EVAL_CHUNK - 1) / EVAL_CHUNK;
-    const unsigned blocks = std::max(1u, div_up(threads, EVAL_THREADS));
-    int rc = ctx->poly_tmp.reserve((size_t)blocks * sizeof(fr));
-    if (rc) return rc;
-    hf::Fr zc = z;
-    for (int i = 0; i < 4; ++i) zc = hf::sqr(zc); // z^16
+    EvalBatchParams P;
+    memset(&P, 0, sizeof(P));
+    size_t n_max = 1;
+    for (size_t k = 0; k < count; ++k) {
+        if (n[k] >= (1ull << 32)) {
+            set_last_error("evaluate: too many coefficients");
+            return BBG_ERR_ARG;
+        }
+        n_max = std::max(n_max, n[k]);
+        P.coeffs[k] = (const fr*)d_coeffs[k];
+        P.n[k] = (uint32_t)n[k];
+        const hf::Fr z = hf::reduce(hf::load((const char*)zs + 32 * k));
+        hf::Fr zc = z;
+        for (int i = 0; i < 4; ++i) zc = hf::sqr(zc); // z^16
+        P.z[k] = dev_fr(z);
+        P.z_chunk[k] = dev_fr(hf::reduce(zc));
+    }
     static_assert(EVAL_CHUNK == 16, "z^EVAL_CHUNK is computed by four squarings");
-    k_eval_partial<<<blocks, EVAL_THREADS, 0, st>>>((const fr*)d_coeffs, (uint32_t)n, dev_fr(hf::reduce(z)), dev_fr(hf::reduce(zc)), (fr*)ctx->poly_tmp.p);
-    k_eval_final<<<1, EVAL_THREADS, 0, st>>>((const fr*)ctx->poly_tmp.p, blocks, (fr*)d_out);
+    const size_t threads = (n_max + EVAL_CHUNK - 1) / EVAL_CHUNK;
+    const unsigned blocks = std::max(1u, div_up(threads, EVAL_THREADS));
+    int rc = ctx->poly_tmp.reserve((size_t)blocks * count * sizeof(fr));
+    if (rc) return rc;
+    k_eval_partial<<<dim3(blocks, (unsigned)count), EVAL_THREADS, 0, st>>>(P, (fr*)ctx->poly_tmp.p);
+    k_eval_final<<<(unsigned)count, EVAL_THREADS, 0, st>>>((const fr*)ctx->poly_tmp.p, blocks, (fr*)d_out);
     ctx->launches += 2;
     BBG_CUDA(cudaGetLastError());
     return BBG_OK;
+}
+
+int poly_evaluate_device(Context* ctx, const void* d_coeffs, size_t n, const hf::Fr& z, void* d_out, cudaStream_t st)
+{
+    return poly_evaluate_batch_device(ctx, &d_coeffs, &n, z.d, 1, d_out, st);
 }
 
 int poly_opening_device(Context* ctx, const void* d_src, size_t n_in, size_t n_out, const hf::Fr& z, void* d_dest, void* d_f_at_z, cudaStream_t st)

@@ -56,6 +56,13 @@ struct GrandParams {
     Fe<FrParams> coset_gen[3];
 };
 
+static constexpr unsigned EVAL_BATCH_MAX = 40;
+struct EvalBatchParams {
+    const Fe<FrParams>* coeffs[EVAL_BATCH_MAX];
+    uint32_t n[EVAL_BATCH_MAX];
+    Fe<FrParams> z[EVAL_BATCH_MAX];
+    Fe<FrParams> z_chunk[EVAL_BATCH_MAX];
+};
 static constexpr unsigned LINCOMB_MAX = 48;
 struct LinCombParams {
     Fe<FrParams>* dest;
@@ -91,6 +98,7 @@ int poly_permutation_quotient_device(Context* ctx, const PermArgs& A, cudaStream
 int poly_divide_vanishing_device(Context* ctx, void* d_q, size_t n_small, size_t n_large, unsigned roots_cut, cudaStream_t st);
 int poly_lagrange_l1_device(Context* ctx, void* d_out, size_t n_small, size_t n_large, cudaStream_t st);
 int poly_grand_product_device(Context* ctx, const GrandArgs& A, cudaStream_t st);
+int poly_evaluate_batch_device(Context* ctx, const void* const* d_coeffs, const size_t* n, const void* zs, size_t count, void* d_out, cudaStream_t st);
 int poly_evaluate_device(Context* ctx, const void* d_coeffs, size_t n, const hf::Fr& z, void* d_out, cudaStream_t st);
 int poly_opening_device(Context* ctx, const void* d_src, size_t n_in, size_t n_out, const hf::Fr& z, void* d_dest, void* d_f_at_z, cudaStream_t st);
 int poly_linear_combination_device(Context* ctx, void* d_dest, const void* d_base, const void* const* d_polys, const void* scalars, size_t count,

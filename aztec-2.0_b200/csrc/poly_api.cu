@@ -337,6 +337,35 @@ int bbg_evaluate(const void* coeffs, size_t n, const void* z, void* result)
     return scope.tm.finish();
 }
 
+// count evaluations in one launch: results[k] = sum_i polys[k][i] z_k^i over ns[k] coefficients (count <= 40)
+int bbg_evaluate_batch(const void* const* polys, const size_t* ns, size_t count, const void* zs, void* results)
+{
+    GET_CTX();
+    StreamScope order(ctx, ctx->stream);
+    if (count == 0) return BBG_OK;
+    if (!polys || !ns || !zs || !results || count > EVAL_BATCH_MAX) {
+        set_last_error("evaluate_batch: null argument or more than 40 polynomials");
+        return BBG_ERR_ARG;
+    }
+    Arg args[EVAL_BATCH_MAX];
+    for (size_t k = 0; k < count; ++k) {
+        args[k].host = polys[k];
+        args[k].bytes = ns[k] * 32;
+    }
+    uint64_t h2d = 0;
+    int rc;
+    if ((rc = bind(ctx, args, (int)count, ctx->stream, &h2d))) return rc;
+    if ((rc = ctx->poly_out.reserve(EVAL_BATCH_MAX * 32))) return rc;
+    PolyScope scope(ctx);
+    const void* d_polys[EVAL_BATCH_MAX];
+    for (size_t k = 0; k < count; ++k) d_polys[k] = args[k].d;
+    if ((rc = poly_evaluate_batch_device(ctx, d_polys, ns, zs, count, ctx->poly_out.p, ctx->stream))) return rc;
+    scope.tm.stop();
+    BBG_CUDA(cudaMemcpyAsync(results, ctx->poly_out.p, count * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    scope.account(h2d, count * 32);
+    return scope.tm.finish();
+}
+
 int bbg_compute_opening_polynomial(const void* src, void* dest, const void* z, size_t n_eval, size_t n, void* f_at_z, unsigned flags)
 {
     GET_CTX();

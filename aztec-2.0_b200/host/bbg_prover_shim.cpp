@@ -14,6 +14,7 @@
 //   polynomial_arithmetic::divide_by_pseudo_vanishing_polynomial                 bb/polynomials/polynomial_arithmetic.cpp:628-725
 //   polynomial_arithmetic::evaluate                                              bb/polynomials/polynomial_arithmetic.cpp:507-538
 //   KateCommitmentScheme<{turbo,unrolled_turbo}_settings>::batch_open            commitment_scheme/kate_commitment_scheme.cpp:133-237
+//   KateCommitmentScheme<{turbo,unrolled_turbo}_settings>::add_opening_evaluations_to_transcript   ... :373-436
 //
 // What changes for a TurboPLONK proof (program width 4; every widget it uses is replaced here):
 //   * work items are submitted in batches: the four wire commitments / four quotient commitments of a round go to
@@ -370,7 +371,73 @@ void batch_open_width4(const transcript::StandardTranscript& transcript, waffle:
     check(bbg_compute_opening_polynomial(&shifted_opening_poly[0], &shifted_opening_poly[0], &zeta_omega, n, n, nullptr, keep));
     queue.add_to_queue({ waffle::work_queue::WorkType::SCALAR_MULTIPLICATION, &shifted_opening_poly[0], "PI_Z_OMEGA", fr(0), 0 });
 }
+
+// every opening evaluation of round 5 in ONE device launch (the reference evaluates the ~30 polynomials one by one)
+template <typename settings>
+void opening_evaluations(transcript::StandardTranscript& transcript, const std::shared_ptr<waffle::proving_key>& input_key,
+                         const std::shared_ptr<waffle::program_witness>& witness, bool in_lagrange_form)
+{
+    Trace trace("add_opening_evaluations_to_transcript");
+    using waffle::PolynomialSource;
+    const fr zeta = fr::serialize_from_buffer(transcript.get_challenge("z").begin());
+    const fr shifted_z = zeta * input_key->small_domain.root;
+    const size_t n = input_key->small_domain.size;
+    std::vector<const void*> polys;
+    std::vector<size_t> ns;
+    std::vector<fr> zs;
+    std::vector<std::string> labels;
+    for (size_t i = 0; i < input_key->polynomial_manifest.size(); ++i) {
+        const auto& info = input_key->polynomial_manifest[i];
+        const std::string poly_label(info.polynomial_label);
+        fr* poly = nullptr;
+        switch (info.source) {
+        case PolynomialSource::WITNESS: poly = &witness->wires.at(poly_label)[0]; break;
+        case PolynomialSource::SELECTOR: poly = &input_key->constraint_selectors.at(poly_label)[0]; break;
+        case PolynomialSource::PERMUTATION: poly = &input_key->permutation_selectors.at(poly_label)[0]; break;
+        }
+        if (!info.is_linearised || !settings::use_linearisation) {
+            polys.push_back(poly);
+            ns.push_back(n);
+            zs.push_back(zeta);
+            labels.push_back(poly_label);
+        }
+        if (info.requires_shifted_evaluation) {
+            polys.push_back(poly);
+            ns.push_back(n);
+            // like the reference (kate_commitment_scheme.cpp:427-431): the Lagrange-form branch evaluates at zeta
+            zs.push_back(in_lagrange_form ? zeta : shifted_z);
+            labels.push_back(poly_label + "_omega");
+        }
+    }
+    std::vector<fr> evals(polys.size());
+    if (in_lagrange_form) {
+        for (size_t k = 0; k < polys.size(); ++k) {
+            evals[k] = barretenberg::polynomial_arithmetic::compute_barycentric_evaluation(const_cast<fr*>(static_cast<const fr*>(polys[k])), n, zs[k], input_key->small_domain);
+        }
+    } else {
+        ensure_resident();
+        for (size_t k = 0; k < polys.size(); k += 40) {
+            const size_t m = std::min<size_t>(40, polys.size() - k);
+            check(bbg_evaluate_batch(polys.data() + k, ns.data() + k, m, zs.data() + k, evals.data() + k));
+        }
+    }
+    for (size_t k = 0; k < polys.size(); ++k) transcript.add_element(labels[k], evals[k].to_buffer());
+}
 } // namespace
+
+#define BBG_KATE_EVALS(NAME, SETTINGS, MANGLED)                                                                                             \
+    extern "C" void NAME(void* self, transcript::StandardTranscript* transcript, std::shared_ptr<waffle::proving_key>* key,                  \
+                         std::shared_ptr<waffle::program_witness>* witness, bool in_lagrange_form) asm(MANGLED);                             \
+    extern "C" void NAME(void*, transcript::StandardTranscript* transcript, std::shared_ptr<waffle::proving_key>* key,                       \
+                         std::shared_ptr<waffle::program_witness>* witness, bool in_lagrange_form)                                           \
+    {                                                                                                                                       \
+        opening_evaluations<SETTINGS>(*transcript, *key, *witness, in_lagrange_form);                                                       \
+    }
+BBG_KATE_EVALS(bbg_shim_opening_evals_turbo, waffle::turbo_settings,
+               "_ZN6waffle20KateCommitmentSchemeINS_14turbo_settingsEE37add_opening_evaluations_to_transcriptERN10transcript18StandardTranscriptESt10shared_ptrINS_11proving_keyEES6_INS_15program_witnessEEb")
+BBG_KATE_EVALS(bbg_shim_opening_evals_unrolled_turbo, waffle::unrolled_turbo_settings,
+               "_ZN6waffle20KateCommitmentSchemeINS_23unrolled_turbo_settingsEE37add_opening_evaluations_to_transcriptERN10transcript18StandardTranscriptESt10shared_ptrINS_11proving_keyEES6_INS_15program_witnessEEb")
+#undef BBG_KATE_EVALS
 
 extern "C" void bbg_shim_batch_open_unrolled_turbo(void* self, const transcript::StandardTranscript* transcript, waffle::work_queue* queue,
                                                    std::shared_ptr<waffle::proving_key>* key, std::shared_ptr<waffle::program_witness>* witness)

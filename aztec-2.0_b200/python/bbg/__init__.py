@@ -37,7 +37,7 @@ EXPORTS = [
     "bbg_pippenger_unsafe_batch", "bbg_pippenger_unsafe_batch_dev", "bbg_pippenger_batch",
     "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_ntt_ex", "bbg_wire_coset_fft", "bbg_turbo_quotient",
     "bbg_permutation_quotient", "bbg_divide_by_pseudo_vanishing_polynomial", "bbg_compute_lagrange_polynomial_fft",
-    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
+    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
 ]
 
 
@@ -121,6 +121,7 @@ lib.bbg_permutation_grand_product.argtypes = [_vp, _vp, ctypes.c_uint, _sz, _vp,
 lib.bbg_evaluate.argtypes = [_vp, _sz, _vp, _vp]
 lib.bbg_compute_opening_polynomial.argtypes = [_vp, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint]
 lib.bbg_poly_write.argtypes = [_vp, _sz, _vp, _sz]
+lib.bbg_evaluate_batch.argtypes = [_vp, _vp, _sz, _vp, _vp]
 lib.bbg_linear_combination.argtypes = [_vp, _vp, _vp, _vp, _sz, _sz, ctypes.c_uint]
 lib.bbg_resident_mode.argtypes = [_int]
 lib.bbg_resident_invalidate.argtypes = [_vp, _sz]
@@ -559,6 +560,18 @@ def evaluate(coeffs, z, n=None):
     out = np.zeros(4, dtype=np.uint64)
     zz = _fr1(z)
     _check(lib.bbg_evaluate(c.ctypes.data, c.shape[0] if n is None else n, zz.ctypes.data, out.ctypes.data))
+    return out
+
+
+def evaluate_batch(polys, zs):
+    """[sum_i polys[k][i] * zs[k]^i] as a (k, 4) array, one launch"""
+    arrs = [_np(a, 4) for a in polys]
+    k = len(arrs)
+    tab = (ctypes.c_void_p * max(k, 1))(*[a.ctypes.data for a in arrs])
+    ns = (ctypes.c_size_t * max(k, 1))(*[a.shape[0] for a in arrs])
+    z = _np(zs, 4)
+    out = np.zeros((k, 4), dtype=np.uint64)
+    _check(lib.bbg_evaluate_batch(ctypes.cast(tab, _vp), ctypes.cast(ns, _vp), k, z.ctypes.data, out.ctypes.data))
     return out
 
 

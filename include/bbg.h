@@ -229,6 +229,10 @@ int bbg_permutation_grand_product(const void* const* wires_lagrange, const void*
                                   const void* beta, const void* gamma, void* z, unsigned flags);
 /* polynomial_arithmetic::evaluate(coeffs, z, n) (:507-538): canonical fr result */
 int bbg_evaluate(const void* coeffs, size_t n, const void* z, void* result);
+/* `count` (<= 40) evaluations in one launch: results[k] = sum_i polys[k][i] * z_k^i over ns[k] coefficients, zs = count
+ * consecutive fr.  KateCommitmentScheme::add_opening_evaluations_to_transcript (kate_commitment_scheme.cpp:373-436) evaluates
+ * every polynomial of the manifest at zeta (and some at zeta * omega) one after the other. */
+int bbg_evaluate_batch(const void* const* polys, const size_t* ns, size_t count, const void* zs, void* results);
 /* KateCommitmentScheme::compute_opening_polynomial / compute_kate_opening_coefficients (commitment_scheme/kate_commitment_scheme.cpp:25-57,
  * polynomial_arithmetic.cpp:727-751): dest[0, n) = coefficients of (F(X) - F(z)) / (X - z), F = src[0, n_eval); *f_at_z = F(z)
  * (may be null); dest may equal src */

@@ -223,3 +223,13 @@ def test_linear_combination_vs_field_ops(bbg, orc, count, with_base):
         buf = base.copy()
         bbg.linear_combination(polys, sc, n, base=buf, dest=buf)
         assert np.array_equal(canon(orc, buf), canon(orc, want))
+
+
+def test_evaluate_batch_vs_reference(bbg, orc, ref):
+    """round 5's opening evaluations in one launch: different lengths and different points per polynomial"""
+    sizes = [4096, 4096, 1 << 14, 33, 4096, 1]
+    polys = [inputs.fr_elements(700 + k, n, coarse_fraction=0.1) for k, n in enumerate(sizes)]
+    zs = inputs.fr_elements(710, len(sizes))
+    got = bbg.evaluate_batch(polys, zs)
+    for k in range(len(sizes)):
+        assert np.array_equal(canon(orc, got[k]), canon(orc, ref.evaluate(polys[k], zs[k]))), k
