@@ -49,12 +49,12 @@ static int create_context(int device)
     if (getenv("BBG_STACK")) BBG_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(getenv("BBG_STACK"))));
     BBG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     BBG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    BBG_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    for (auto& a : c->aux_stream) BBG_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
     for (auto& e : c->ev_piece) BBG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     BBG_CUDA(cudaEventCreate(&c->ev_a));
     BBG_CUDA(cudaEventCreate(&c->ev_b));
     BBG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    BBG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    for (auto& e : c->ev_join) BBG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     BBG_CUDA(cudaEventCreateWithFlags(&c->last_use, cudaEventDisableTiming));
     g_ctx = c;
     return BBG_OK;
@@ -437,11 +437,11 @@ void bbg_shutdown(void)
     cudaEventDestroy(g_ctx->ev_a);
     cudaEventDestroy(g_ctx->ev_b);
     cudaEventDestroy(g_ctx->ev_fork);
-    cudaEventDestroy(g_ctx->ev_join);
+    for (auto& e : g_ctx->ev_join) cudaEventDestroy(e);
     cudaEventDestroy(g_ctx->last_use);
     cudaStreamDestroy(g_ctx->stream);
     cudaStreamDestroy(g_ctx->copy_stream);
-    cudaStreamDestroy(g_ctx->aux_stream);
+    for (auto& a : g_ctx->aux_stream) cudaStreamDestroy(a);
     for (auto& e : g_ctx->ev_piece) cudaEventDestroy(e);
     delete g_ctx;
     g_ctx = nullptr;
@@ -729,18 +729,22 @@ int bbg_pippenger_unsafe_dev(void* pippenger, const void* d_scalars, size_t from
 }
 
 // Several MSMs over the same bases in one call (the prover commits to its four wire polynomials, then to the four
-// slices of the quotient polynomial, back to back: prover.cpp:66-82, 84-135).  MSM i runs on stream i & 1 with workspace
-// i & 1, so the latency-bound tail of one MSM (slot merge, bucket reduction: a few hundred lone warps) overlaps the
-// throughput-bound bucket accumulation of the next.
+// slices of the quotient polynomial, back to back: prover.cpp:66-82, 84-135).  MSM i runs on stream i mod 4 with workspace
+// i mod 4, so the latency-bound tail of one MSM (slot merge, bucket reduction: a few hundred warps) overlaps the
+// throughput-bound bucket accumulation of the next ones.
 static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, bool device_scalars, size_t count, size_t from,
                      size_t range, void* results, bool device_results, cudaStream_t st0)
 {
     int rc;
     StreamScope order(ctx, st0);
-    cudaStream_t st[2] = { st0, ctx->aux_stream };
-    if (count > 1) {
+    constexpr int WAYS = Context::BATCH_WAYS;
+    cudaStream_t st[WAYS];
+    st[0] = st0;
+    for (int k = 1; k < WAYS; ++k) st[k] = ctx->aux_stream[k - 1];
+    const int used = (int)std::min<size_t>(count, WAYS);
+    if (used > 1) {
         BBG_CUDA(cudaEventRecord(ctx->ev_fork, st0));
-        BBG_CUDA(cudaStreamWaitEvent(st[1], ctx->ev_fork, 0));
+        for (int k = 1; k < used; ++k) BBG_CUDA(cudaStreamWaitEvent(st[k], ctx->ev_fork, 0));
     }
     uint64_t h2d = 0;
     StatScope stat(STAT_MSM, ctx, 0, device_results ? 0 : 96 * count);
@@ -756,8 +760,8 @@ static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, 
         ctx->pinned_cap = cap;
     }
     for (size_t i = 0; i < count; ++i) {
-        MsmWorkspace& ws = ctx->msm_ws[i & 1];
-        cudaStream_t s = st[i & 1];
+        MsmWorkspace& ws = ctx->msm_ws[i % WAYS];
+        cudaStream_t s = st[i % WAYS];
         const void* d_sc = scalars[i];
         if (!device_scalars) {
             void* d_res = nullptr;
@@ -783,9 +787,9 @@ static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, 
     }
     if (stat.row) stat.row->bytes_h2d += h2d;
     stat.h2d = h2d;
-    if (count > 1) {
-        BBG_CUDA(cudaEventRecord(ctx->ev_join, st[1]));
-        BBG_CUDA(cudaStreamWaitEvent(st0, ctx->ev_join, 0));
+    for (int k = 1; k < used; ++k) {
+        BBG_CUDA(cudaEventRecord(ctx->ev_join[k - 1], st[k]));
+        BBG_CUDA(cudaStreamWaitEvent(st0, ctx->ev_join[k - 1], 0));
     }
     if (!device_results) {
         BBG_CUDA(cudaStreamSynchronize(st0));

@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace bbg {
@@ -77,8 +78,8 @@ struct Profiler {
     }
 };
 
-// Everything one MSM in flight needs.  The context owns two, so that a batch (bbg_msm_batch) can run MSM i + 1 on a
-// second stream while the latency-bound tail of MSM i (slot merge, bucket reduction) is still draining.
+// Everything one MSM in flight needs.  The context owns four, so that a batch (bbg_pippenger*_batch) can run MSM i + 1 ..
+// i + 3 on other streams while the latency-bound tail of MSM i (slot merge, bucket reduction) is still draining.
 struct MsmWorkspace {
     DevBuf scalars, counts, offsets, cursors, sorted, buckets, partials, reduce, scan_tmp, result, lvl_offsets, pairs_a, pairs_b,
         pair_pre, pair_meta, pts0;
@@ -95,10 +96,11 @@ struct Context {
     int num_sms = 148;
     cudaStream_t stream = nullptr; // default work stream for the host-pointer entry points
     cudaStream_t copy_stream = nullptr; // H2D pieces that overlap with kernels on `stream`
-    cudaStream_t aux_stream = nullptr;  // second work stream of the batched entry points
+    static constexpr int BATCH_WAYS = 4;
+    cudaStream_t aux_stream[BATCH_WAYS - 1] = {}; // extra work streams of the batched entry points
     cudaEvent_t ev_piece[8] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join[BATCH_WAYS - 1] = {};
     // Cross-stream ordering of the shared workspaces and cached tables: every call records `last_use` on its stream when
     // it has queued its work, and a call on a DIFFERENT stream first waits for it (StreamScope in internal.hpp).  Calls on
     // different streams therefore serialise on the device; they never race on the workspaces.
@@ -106,7 +108,7 @@ struct Context {
     cudaStream_t last_stream = nullptr;
     bool last_valid = false;
     // MSM workspaces
-    MsmWorkspace msm_ws[2];
+    MsmWorkspace msm_ws[BATCH_WAYS];
     DevBuf msm_points;
     void* inv_fix_fq = nullptr; // inv.cuh fix-up constants (fq)
     // NTT workspaces
@@ -146,6 +148,7 @@ struct Context {
         uint64_t sample_val[SAMPLES];
     };
     std::vector<Resident> resident;
+    std::vector<std::pair<void*, size_t>> resident_free; // retired device blocks (pointer, capacity) awaiting reuse
     int resident_mode = -1; // -1: read BBG_RESIDENT on first use; 0 off; 1 on
     size_t resident_bytes = 0, resident_budget = 0;
     uint64_t resident_clock = 0;

@@ -61,6 +61,7 @@ void resident_invalidate(Context* ctx, const void* host, size_t bytes);
 int resident_flush(Context* ctx, const void* host, size_t bytes, cudaStream_t st);
 // true when a mirror containing the range holds data newer than host memory (a deferred write-back is pending)
 bool resident_is_ahead(Context* ctx, const void* host, size_t bytes);
+void resident_adopt(Context* ctx, const void* host, size_t bytes);
 void resident_clear(Context* ctx);
 
 // ntt.cu

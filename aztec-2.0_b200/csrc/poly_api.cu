@@ -478,6 +478,39 @@ int bbg_wire_coset_fft(const void* wire, void* wire_fft, size_t n, size_t ext, u
     return scope.tm.finish();
 }
 
+// work_queue IFFT item (work_queue.hpp:272-276) for a wire whose Lagrange-base copy the prover keeps in `lagrange_copy`:
+// wire <- ifft(wire) in place, and the device mirror of lagrange_copy[0, n) is seeded from the data uploaded for the
+// transform (prover.cpp:184-186 memcpy'd it from `wire` just before), so round 3's grand product finds it on the device
+int bbg_wire_ifft(void* wire, size_t n, const void* lagrange_copy)
+{
+    GET_CTX();
+    StreamScope order(ctx, ctx->stream);
+    if (!wire || n == 0 || (n & (n - 1))) {
+        set_last_error("wire_ifft: null argument or n not a power of two");
+        return BBG_ERR_ARG;
+    }
+    Arg args[2];
+    args[0].host = wire;
+    args[0].bytes = n * 32;
+    args[0].written = true;
+    args[1].host = lagrange_copy;
+    args[1].bytes = n * 32;
+    args[1].need_data = false;
+    uint64_t h2d = 0, d2h = 0;
+    int rc;
+    if ((rc = bind(ctx, args, 2, ctx->stream, &h2d))) return rc;
+    PolyScope scope(ctx);
+    if (lagrange_copy != nullptr && args[1].resident) {
+        BBG_CUDA(cudaMemcpyAsync(args[1].d, args[0].d, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        resident_adopt(ctx, lagrange_copy, n * 32);
+    }
+    if ((rc = ntt_run_kind(ctx, args[0].d, n, BBG_IFFT, 0, nullptr, ctx->stream))) return rc;
+    scope.tm.stop();
+    if ((rc = finish(ctx, args, 2, 0, ctx->stream, &d2h))) return rc;
+    scope.account(h2d, d2h);
+    return scope.tm.finish();
+}
+
 // host[elem_offset, elem_offset + count) = values, in host memory AND in the array's device mirror if it has one
 // (the prover's blinding scalars, prover.cpp:181-183 / permutation_widget_impl.hpp:289-291, written between two device steps)
 int bbg_poly_write(void* host_array, size_t elem_offset, const void* values, size_t count)

@@ -92,12 +92,55 @@ static int write_back(Context* ctx, Context::Resident& e, cudaStream_t st)
     return BBG_OK;
 }
 
+// A retired mirror's device block goes to a small free list instead of back to the driver: a prover allocates fresh
+// host arrays for every proof (witness wires, z), so mirrors of the same few sizes are created and orphaned all the time,
+// and cudaMalloc / cudaFree cost 0.1-1 ms apiece (they synchronise).  Blocks are only ever reused by work queued on the
+// library's streams AFTER the work that last touched them, so no synchronisation is needed here.
+static constexpr size_t RESIDENT_MAX_ENTRIES = 192;
+static constexpr size_t RESIDENT_FREE_BLOCKS = 32;
 static void drop(Context* ctx, size_t idx)
 {
     Context::Resident& e = ctx->resident[idx];
-    if (e.d) cudaFree(e.d);
-    ctx->resident_bytes -= e.cap;
+    if (e.d) {
+        if (ctx->resident_free.size() < RESIDENT_FREE_BLOCKS) {
+            ctx->resident_free.push_back({ e.d, e.cap });
+        } else {
+            cudaFree(e.d);
+            ctx->resident_bytes -= e.cap;
+        }
+    }
     ctx->resident.erase(ctx->resident.begin() + (long)idx);
+}
+static void* take_block(Context* ctx, size_t bytes, size_t* cap)
+{
+    auto& fl = ctx->resident_free;
+    size_t best = fl.size();
+    for (size_t i = 0; i < fl.size(); ++i) {
+        if (fl[i].second >= bytes && fl[i].second <= 2 * bytes && (best == fl.size() || fl[i].second < fl[best].second)) best = i;
+    }
+    if (best != fl.size()) {
+        void* p = fl[best].first;
+        *cap = fl[best].second;
+        fl.erase(fl.begin() + (long)best);
+        return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        // make room by returning the free list to the driver, then try once more
+        for (auto& b : fl) {
+            cudaFree(b.first);
+            ctx->resident_bytes -= b.second;
+        }
+        fl.clear();
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
+    *cap = bytes;
+    ctx->resident_bytes += bytes;
+    return p;
 }
 
 int resident_acquire(Context* ctx, const void* host_v, size_t bytes, bool need_data, void** d_out, bool* hit, cudaStream_t st)
@@ -136,41 +179,40 @@ int resident_acquire(Context* ctx, const void* host_v, size_t bytes, bool need_d
     // bbg_resident_flush), i.e. by a caller that vouches for it.
     for (size_t i = tab.size(); i-- > 0;) {
         Context::Resident& e = tab[i];
-        if (host < e.host + e.bytes && e.host < host + bytes) {
-            BBG_CUDA(cudaStreamSynchronize(st));
-            drop(ctx, i);
-        }
+        if (host < e.host + e.bytes && e.host < host + bytes) drop(ctx, i);
     }
     // room: evict least-recently-used mirrors; mirrors that are ahead of host memory hold the only copy and stay
     const size_t budget = resident_budget(ctx);
-    while (ctx->resident_bytes + bytes > budget) {
+    while (ctx->resident_bytes + bytes > budget || tab.size() >= RESIDENT_MAX_ENTRIES) {
         size_t victim = tab.size();
         for (size_t i = 0; i < tab.size(); ++i) {
             if (tab[i].host_stale) continue;
             if (victim == tab.size() || tab[i].last_use < tab[victim].last_use) victim = i;
         }
         if (victim == tab.size()) break; // nothing evictable: this array is simply not mirrored
-        BBG_CUDA(cudaStreamSynchronize(st));
         drop(ctx, victim);
+        if (ctx->resident_bytes + bytes > budget && !ctx->resident_free.empty()) {
+            // over the byte budget: the block really goes back to the driver
+            for (auto& b : ctx->resident_free) {
+                cudaFree(b.first);
+                ctx->resident_bytes -= b.second;
+            }
+            ctx->resident_free.clear();
+        }
     }
-    if (ctx->resident_bytes + bytes > budget) return BBG_OK;
+    if (ctx->resident_bytes + bytes > budget || tab.size() >= RESIDENT_MAX_ENTRIES) return BBG_OK;
     if (bytes > budget) return BBG_OK; // too large to mirror: caller stages as before
     Context::Resident e;
     e.host = host;
     e.bytes = bytes;
-    if (cudaMalloc(&e.d, bytes) != cudaSuccess) {
-        cudaGetLastError();
-        return BBG_OK; // out of memory: not resident
-    }
-    e.cap = bytes;
+    e.d = take_block(ctx, bytes, &e.cap);
+    if (e.d == nullptr) return BBG_OK; // out of memory: not resident
     e.last_use = now;
     plan_samples(e);
-    ctx->resident_bytes += e.cap;
     if (need_data) {
         ctx->resident_misses += 1;
         if ((rc = g_staging.h2d(e.d, host, bytes, st))) {
-            cudaFree(e.d);
-            ctx->resident_bytes -= e.cap;
+            ctx->resident_free.push_back({ e.d, e.cap });
             return rc;
         }
         take_samples(e, 0, bytes);
@@ -231,6 +273,21 @@ int resident_flush(Context* ctx, const void* host_v, size_t bytes, cudaStream_t 
     return BBG_OK;
 }
 
+// The caller vouches that host bytes [host, host + bytes) currently equal what `st` has just put into the mirror of that
+// range (a device-to-device copy of data uploaded for another array): fingerprint the range from host memory so that
+// later lookups find it valid.
+void resident_adopt(Context* ctx, const void* host_v, size_t bytes)
+{
+    const char* host = (const char*)host_v;
+    for (Context::Resident& e : ctx->resident) {
+        if (host >= e.host && host + bytes <= e.host + e.bytes) {
+            const size_t lo = (size_t)(host - e.host);
+            take_samples(e, lo, lo + bytes);
+            return;
+        }
+    }
+}
+
 bool resident_is_ahead(Context* ctx, const void* host_v, size_t bytes)
 {
     const char* host = (const char*)host_v;
@@ -245,7 +302,9 @@ void resident_clear(Context* ctx)
     for (Context::Resident& e : ctx->resident) {
         if (e.d) cudaFree(e.d);
     }
+    for (auto& b : ctx->resident_free) cudaFree(b.first);
     ctx->resident.clear();
+    ctx->resident_free.clear();
     ctx->resident_bytes = 0;
 }
 

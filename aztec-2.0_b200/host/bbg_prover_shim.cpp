@@ -258,7 +258,11 @@ extern "C" void bbg_shim_process_queue(waffle::work_queue* self)
             polynomial& wire = witness->wires.at(item.tag);
             polynomial& wire_fft = key->wire_ffts.at(item.tag + "_fft");
             check(bbg_resident_invalidate(&wire_fft[0], wire_fft.get_max_size() * sizeof(fr)));
-            wire.ifft(key->small_domain); // -> polynomial_arithmetic::ifft -> bbg_ntt: uploaded once, mirror kept
+            // what polynomial::ifft does (polynomial.cpp:312-320), plus: the upload also seeds the mirror of the Lagrange
+            // copy in wire_fft[0, n), which round 3's grand product reads
+            if (n > wire.get_max_size()) wire.reserve(n);
+            check(bbg_wire_ifft(&wire[0], n, &wire_fft[0]));
+            wire.resize_unsafe(n);
             ++i;
             break;
         }

@@ -37,7 +37,7 @@ EXPORTS = [
     "bbg_pippenger_unsafe_batch", "bbg_pippenger_unsafe_batch_dev", "bbg_pippenger_batch",
     "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_ntt_ex", "bbg_wire_coset_fft", "bbg_turbo_quotient",
     "bbg_permutation_quotient", "bbg_divide_by_pseudo_vanishing_polynomial", "bbg_compute_lagrange_polynomial_fft",
-    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
+    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_wire_ifft", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
 ]
 
 
@@ -121,6 +121,7 @@ lib.bbg_permutation_grand_product.argtypes = [_vp, _vp, ctypes.c_uint, _sz, _vp,
 lib.bbg_evaluate.argtypes = [_vp, _sz, _vp, _vp]
 lib.bbg_compute_opening_polynomial.argtypes = [_vp, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint]
 lib.bbg_poly_write.argtypes = [_vp, _sz, _vp, _sz]
+lib.bbg_wire_ifft.argtypes = [_vp, _sz, _vp]
 lib.bbg_evaluate_batch.argtypes = [_vp, _vp, _sz, _vp, _vp]
 lib.bbg_linear_combination.argtypes = [_vp, _vp, _vp, _vp, _sz, _sz, ctypes.c_uint]
 lib.bbg_resident_mode.argtypes = [_int]
@@ -600,6 +601,11 @@ def linear_combination(polys, scalars, n, base=None, dest=None, flags=0):
 def wire_coset_fft(wire, wire_fft, n, ext=4, flags=0):
     _check(lib.bbg_wire_coset_fft(wire.ctypes.data, wire_fft.ctypes.data, n, ext, flags))
     return wire_fft
+
+
+def wire_ifft(wire, lagrange_copy=None):
+    _check(lib.bbg_wire_ifft(wire.ctypes.data, wire.size // 4, None if lagrange_copy is None else lagrange_copy.ctypes.data))
+    return wire
 
 
 def poly_write(host_array, elem_offset, values):

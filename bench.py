@@ -592,6 +592,8 @@ def run_ours(args):
                 per[name] = nn / (sum(tt) / len(tt))
             cb["ntt"] = {"value": statistics.mean(per.values()), "unit": "elements/s", "per_kind": per, "sample": nsample}
         line["cpu_baseline"] = cb
+        if not args.no_sweep:
+            line["prover"] = prover_record()
     elif rank == 0:
         line["cpu_baseline"] = None
 
@@ -809,6 +811,57 @@ def config1(env, bases, K):
             "unit": "points/s", "e2e": {"value": n / e2e, "ms_per_step": e2e * 1e3, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 96,
                                        "host_memory": "pageable"},
             "result_affine_x0": int(bbg.g1_normalize(r.reshape(1, 12))[0][0])}
+
+
+def prover_record(reps_gpu=6, reps_cpu=3):
+    """BASELINE configs[3]: the reference's TurboPLONK join-split prover (n = 2^16) with its hot path resolved to libbbg.
+    The CALLER is the unmodified reference prover, built as a test harness under oracle/_ref (oracle/js_harness.cpp, three link
+    flavours); the thing measured is this repository's library and shims underneath it.  Proof bytes are compared with the
+    all-CPU build in the same run."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    srs = os.path.join(ref, "srs_db")
+    bins = {k: os.path.join(ref, k) for k in ("js_prover_gpu", "js_prover_gpu_l1", "js_prover_cpu")}
+    if not all(os.path.exists(b) for b in bins.values()) or not os.path.exists(os.path.join(srs, "transcript00.dat")):
+        return {"unavailable": "oracle/_ref/js_prover_* not built (needs the reference tree at build time)"}
+
+    def run(binary, reps, env=None):
+        e = dict(os.environ)
+        e.update(env or {})
+        p = subprocess.run([bins[binary], srs, str(reps)], capture_output=True, text=True, env=e, timeout=600)
+        if p.returncode != 0:
+            return None, p.stderr[-300:]
+        d = json.loads(p.stdout.strip().splitlines()[-1])
+        stats = {}
+        for line in p.stderr.splitlines():
+            if line.startswith('{"bbg_stats"'):
+                st = json.loads(line)
+                stats[st["bbg_stats"]] = st
+        return d, stats
+    out = {"circuit": "rollup::proofs::join_split (63 398 gates, n = 2^16), noop transaction, deterministic engine"}
+    ref_proof = None
+    for name, reps, env in (("js_prover_cpu", reps_cpu, {}), ("js_prover_gpu_l1", reps_gpu, {"BBG_STATS": "1"}), ("js_prover_gpu", reps_gpu, {"BBG_STATS": "1"})):
+        d, stats = run(name, reps, env)
+        if d is None:
+            out[name] = {"error": stats}
+            continue
+        times = [p["construct_proof_s"] for p in d["proofs"]]
+        steady = sorted(times[2:] if len(times) > 3 else times)
+        rec = {"construct_proof_ms_all": [round(t * 1e3, 3) for t in times], "construct_proof_ms": steady[len(steady) // 2] * 1e3,
+               "keygen_s": d["keygen_s"], "keygen_warm_s": d.get("keygen_warm_s"), "cuda_init_s": d.get("cuda_init_s"), "verified": d["verified"],
+               "kernel_launches": d["gpu_kernel_launches"]}
+        if stats:
+            n_proofs = len(times)
+            rec["pcie_bytes_whole_run"] = {k: {"h2d": v["h2d_bytes"], "d2h": v["d2h_bytes"], "calls": v["calls"]} for k, v in stats.items()}
+        if name == "js_prover_cpu":
+            ref_proof = d["first_proof"]
+        else:
+            rec["first_proof_identical_to_cpu"] = (ref_proof is not None and d["first_proof"] == ref_proof)
+        out[name] = rec
+    try:
+        out["speedup_vs_cpu"] = out["js_prover_cpu"]["construct_proof_ms"] / out["js_prover_gpu"]["construct_proof_ms"]
+    except Exception:
+        pass
+    return out
 
 
 def ntt_passes(lg):

@@ -104,8 +104,8 @@ int bbg_pippenger_unsafe_dev(void* pippenger, const void* d_scalars, size_t from
 
 /* `count` MSMs over the same monomials [from, from+range) in one call: what work_queue::process_queue
  * (bb/plonk/proof_system/prover/work_queue.hpp:213-243) does item by item for the prover's W_1..W_4 and T_1..T_4
- * commitments.  scalars[i]: `range` fr elements; results: count x 96 B g1::element.  Consecutive MSMs run on two
- * streams / two workspaces so the latency-bound tail of one overlaps the bucket accumulation of the next. */
+ * commitments.  scalars[i]: `range` fr elements; results: count x 96 B g1::element.  Consecutive MSMs run on up to
+ * four streams / workspaces so the latency-bound tail of one overlaps the bucket accumulation of the next ones. */
 int bbg_pippenger_unsafe_batch(void* pippenger, const void* const* scalars, size_t count, size_t from, size_t range, void* results);
 int bbg_pippenger_unsafe_batch_dev(void* pippenger, const void* const* d_scalars, size_t count, size_t from, size_t range,
                                    void* d_results, void* stream);
@@ -202,6 +202,11 @@ int bbg_domain_constants(size_t n, void* out6);
  * FFT of the n coefficients in `wire` (zero padded, generator_size = n), followed by its first `ext` values again
  * (polynomial::add_lagrange_base_coefficient x ext) */
 int bbg_wire_coset_fft(const void* wire, void* wire_fft, size_t n, size_t ext, unsigned flags);
+/* work_queue IFFT item (work_queue.hpp:272-276): wire <- ifft(wire), in place, n coefficients.  `lagrange_copy` (may be null):
+ * a host array whose first n elements the caller has just copied from `wire` (prover.cpp:184-186 keeps the Lagrange-base
+ * wires in w_i_fft[0, n) for the permutation widget); with resident polynomials its device mirror is seeded from the data
+ * uploaded for the transform instead of being uploaded again in round 3. */
+int bbg_wire_ifft(void* wire, size_t n, const void* lagrange_copy);
 /* TransitionWidget::compute_quotient_contribution (bb/plonk/proof_system/widgets/transition_widgets/transition_widget.hpp:293-307)
  * for the TurboPLONK gate kernels: quotient[i] += identity(i) over the n_large-point coset domain.
  * polys: BBG_NUM_POLYNOMIALS pointers indexed like waffle::PolynomialIndex (types/polynomial_manifest.hpp:10-50) to the

@@ -37,4 +37,43 @@ for lg in ((6, 10) if small else (6, 10, 13, 17)):
         buf = np.zeros((4 << lg, 4), dtype=np.uint64)  # the extended coset FFT writes ext * n elements
         buf[: 1 << lg] = x
         bbg.coset_fft_ext(buf, 1 << lg, 4)
-print("sanitize_run ok", hex(int(s[0])), bbg.kernel_launches(), "launches")
+# ---- round 2: batched MSMs (all four workspaces / streams), tiny MSM (team kernels with S > 1), quotient-stage kernels,
+# scans, resident chain with deferred write-back
+rb = pip.pippenger_unsafe_batch([sc, same, sc[::-1].copy(), sc, same], 0, n)
+pts = bbg.read_transcript_g1(64, inputs.SRS_MINI_DIR)
+r6 = bbg.msm_points(sc[:33], pts[:33])
+ns, nl = 1 << 8, 1 << 10
+ids = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 29, 30, 31, 32]  # Q_1..Q_C, arithmetic / fixed-base / range / logic selectors, W_1..W_4
+polys = {k: inputs.fr_elements(100 + k, nl) for k in ids}
+a0, a1, beta, gamma, delta = (inputs.fr_elements(200 + k, 1)[0] for k in range(5))
+for mode in (False, True):
+    bbg.resident_mode(mode)
+    keep, ahead = (bbg.KEEP_ON_DEVICE, bbg.KEEP_IF_AHEAD) if mode else (0, 0)
+    coeffs = [inputs.fr_elements(300 + k, ns) for k in range(4)]
+    wf = [np.zeros((nl + 4, 4), dtype=np.uint64) for _ in range(4)]
+    for k in range(4):
+        wf[k][:ns] = coeffs[k]
+        bbg.wire_ifft(coeffs[k], wf[k])
+    sig_l = [inputs.fr_elements(310 + k, ns) for k in range(4)]
+    z = bbg.permutation_grand_product([w[:ns] for w in wf], sig_l, ns, beta, gamma, flags=keep)
+    bbg.poly_write(z, ns - 3, inputs.fr_elements(320, 3))
+    bbg.ifft(z)
+    for k in range(4):
+        bbg.wire_coset_fft(coeffs[k], wf[k], ns, 4, keep)
+    p = dict(polys)
+    for k, idx in enumerate((29, 30, 31, 32)):
+        p[idx] = wf[k]
+    q = np.zeros((nl, 4), dtype=np.uint64)
+    sig_f = [inputs.fr_elements(330 + k, nl) for k in range(4)]
+    bbg.permutation_quotient(wf, sig_f, inputs.fr_elements(340, nl), bbg.compute_lagrange_polynomial_fft(ns, nl), nl, 4, a0, beta, gamma, delta, q, keep)
+    for kind in range(4):
+        bbg.turbo_quotient(kind, p, nl, a0, a1, q, ahead)
+    bbg.divide_by_pseudo_vanishing_polynomial(q, ns, 4, ahead)
+    bbg.coset_ifft(q)
+    ev = bbg.evaluate_batch([q, coeffs[0], z], inputs.fr_elements(350, 3))
+    op = np.zeros((ns, 4), dtype=np.uint64)
+    bbg.linear_combination(coeffs, inputs.fr_elements(360, 4), ns, base=q[:ns], dest=op, flags=keep)
+    bbg.compute_opening_polynomial(op, a1, dest=op, flags=keep)
+    r7 = pip.pippenger_unsafe(op, 0, ns)
+bbg.resident_mode(False)
+print("sanitize_run ok", hex(int(s[0])), hex(int(r7[0])), bbg.kernel_launches(), "launches")

@@ -233,3 +233,27 @@ def test_evaluate_batch_vs_reference(bbg, orc, ref):
     got = bbg.evaluate_batch(polys, zs)
     for k in range(len(sizes)):
         assert np.array_equal(canon(orc, got[k]), canon(orc, ref.evaluate(polys[k], zs[k]))), k
+
+
+def test_wire_ifft_seeds_the_lagrange_mirror(bbg, orc, ref):
+    """the IFFT work item keeps the Lagrange-base copy on the device for round 3's grand product"""
+    n = 1 << 10
+    lag = [inputs.fr_elements(800 + k, n) for k in range(4)]
+    sigmas = [inputs.fr_elements(810 + k, n) for k in range(4)]
+    beta, gamma = inputs.fr_elements(820, 1)[0], inputs.fr_elements(821, 1)[0]
+    want_z = bbg.permutation_grand_product(lag, sigmas, n, beta, gamma)
+    bbg.resident_mode(True)
+    try:
+        wires = [w.copy() for w in lag]
+        copies = [np.zeros((4 * n + 4, 4), dtype=np.uint64) for _ in range(4)]
+        for k in range(4):
+            copies[k][:n] = wires[k]           # prover.cpp:184-186
+            bbg.wire_ifft(wires[k], copies[k])
+        s0 = bbg.resident_stats()
+        z = bbg.permutation_grand_product([c[:n] for c in copies], sigmas, n, beta, gamma)
+        assert bbg.resident_stats()["hits"] >= s0["hits"] + 4   # the four Lagrange copies were not uploaded again
+        for k in range(4):
+            assert np.array_equal(canon(orc, wires[k]), canon(orc, ref.ntt(po.NTT_IFFT, lag[k])))
+    finally:
+        bbg.resident_mode(False)
+    assert np.array_equal(canon(orc, z), canon(orc, want_z))
