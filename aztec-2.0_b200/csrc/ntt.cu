@@ -19,6 +19,9 @@
 // HBM traffic: P reads + P writes of the array (+ one 32-byte twiddle per element per inner pass);
 // arithmetic: (log2 N)/2 + P - 1 (+ scalings) Montgomery multiplies per element -- the kernel is
 // bound by the integer pipe (IMAD.WIDE), not by HBM; see DESIGN.md.
+#include <cuda/barrier>
+#include <cuda/ptx>
+
 #include "ctx.cuh"
 #include "field.cuh"
 #include "internal.hpp"
@@ -153,7 +156,17 @@ __device__ __forceinline__ void bfly_notw(fr& u, fr& v)
 // LOGE (or fewer) DIF stages on the E registers x[j], j = LOGE-bit value of row bits [w0, w0 + LOGE).
 // Stages run for row bits b_hi, b_hi-1, ..., w0 (b_hi <= w0 + LOGE - 1). lo = row bits below w0.
 // Stage s (row bit w0 + s) pairs j with j + 2^s; its twiddle exponent is ((j mod 2^s) << w0 | lo) << (g-1-w0-s).
-template <int LOGE>
+// SMEM_TW: the stage twiddles were staged into shared memory by TMA (cp.async.bulk) at kernel start; otherwise they are read
+// from global memory through the read-only path.
+template <bool SMEM_TW> __device__ __forceinline__ fr load_tw(const fr* p)
+{
+    if constexpr (SMEM_TW) {
+        return fe_load<FrParams>(p);
+    } else {
+        return fe_load_nc<FrParams>(p);
+    }
+}
+template <int LOGE, bool SMEM_TW = false>
 __device__ __forceinline__ void radix_round(fr (&x)[1 << LOGE], uint32_t g, uint32_t w0, uint32_t b_hi, uint32_t lo,
                                             const fr* __restrict__ stage_tw)
 {
@@ -174,7 +187,7 @@ __device__ __forceinline__ void radix_round(fr (&x)[1 << LOGE], uint32_t g, uint
                     }
                 } else {
                     const uint32_t e = (((uint32_t)v << w0) | lo) << sh;
-                    fr w = fe_load_nc<FrParams>(stage_tw + e);
+                    fr w = load_tw<SMEM_TW>(stage_tw + e);
 #pragma unroll
                     for (int u = 0; u < (1 << (LOGE - 1 - s)); ++u) {
                         const int j = (u << (s + 1)) | v;
@@ -239,19 +252,44 @@ __device__ __forceinline__ void radix8_round(fr (&x)[8], uint32_t g, uint32_t w0
     }
 }
 
-template <> __device__ __forceinline__ void radix_round<3>(fr (&x)[8], uint32_t g, uint32_t w0, uint32_t b_hi, uint32_t lo,
-                                                            const fr* __restrict__ stage_tw)
+template <> __device__ __forceinline__ void radix_round<3, false>(fr (&x)[8], uint32_t g, uint32_t w0, uint32_t b_hi, uint32_t lo,
+                                                                   const fr* __restrict__ stage_tw)
 {
     radix8_round(x, g, w0, b_hi, lo, stage_tw); // hand-unrolled form: ptxas spills less with it than with the generic loops
 }
 
 // LAST is a template parameter so that each flavour only carries its own index maths in registers
-template <int LOGE, bool LAST>
-__global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pass(const PassParams P)
+// TMA_TW: one thread issues a TMA bulk copy (cp.async.bulk, completion on an mbarrier) of this pass's stage-twiddle table
+// (2^(g-1) entries, <= 4 KB) into shared memory behind the exchange buffer; the copy flies while the threads load their
+// elements from HBM, and the radix rounds then read twiddles from shared memory instead of the L1 / read-only path.
+static constexpr int NTT_TW_SMEM_BYTES = 128 * 32;
+template <int LOGE, bool LAST, int CTAS = NttGeom<LOGE>::MIN_CTAS, bool TMA_TW = false>
+__global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams P)
 {
     extern __shared__ uint4 sm[];
     constexpr int E = NttGeom<LOGE>::E;
     const uint32_t half_stride = NttGeom<LOGE>::HALF_STRIDE;
+    using tw_barrier = cuda::barrier<cuda::thread_scope_block>;
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ tw_barrier tw_bar;
+    const fr* stage_tw = P.stage_tw;
+    tw_barrier::arrival_token tw_token;
+    if constexpr (TMA_TW) {
+        fr* tw_sm = reinterpret_cast<fr*>(sm + 2 * NttGeom<LOGE>::HALF_STRIDE);
+        const uint32_t tw_bytes = 32u << (P.g - 1);
+        if (threadIdx.x == 0) {
+            init(&tw_bar, NTT_THREADS);
+            cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            cuda::device::memcpy_async_tx(tw_sm, P.stage_tw, cuda::aligned_size_t<16>(tw_bytes), tw_bar);
+            tw_token = cuda::device::barrier_arrive_tx(tw_bar, 1, tw_bytes);
+        } else {
+            tw_token = tw_bar.arrive();
+        }
+        stage_tw = tw_sm;
+    }
 
     const uint32_t g = P.g;
     const uint32_t R = 1u << g;                   // rows per tile
@@ -260,25 +298,25 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
     const uint32_t tau = threadIdx.x & (R - 1);
     const uint32_t col = tau & (E - 1);
     const uint32_t q = tau >> LOGE;               // [0, R/E)
-    const uint64_t N = 1ull << P.tw_log_n;                  // full transform (twiddle exponents)
-    const uint64_t num_tiles = (1ull << P.log_n) >> (g + LOGE); // local array
-    const uint64_t tile = (uint64_t)blockIdx.x * tiles_per_cta + tile_local;
+    const uint32_t Nmask = (1u << P.tw_log_n) - 1u;         // full transform (twiddle exponents); n <= 2^28: 32-bit index maths throughout
+    const uint32_t num_tiles = (1u << P.log_n) >> (g + LOGE); // local array
+    const uint32_t tile = blockIdx.x * tiles_per_cta + tile_local;
     const bool active = tile < num_tiles;
     const uint32_t rows8 = R >> LOGE;
 
     // ---- tile coordinates
-    uint64_t in_base = 0;     // address of (row 0, col 0)
-    uint64_t rest0 = 0;       // non-last: first value of the low index; last: first o_1 of the tile
-    uint64_t mid = 0;
+    uint32_t in_base = 0;     // element index of (row 0, col 0)
+    uint32_t rest0 = 0;       // non-last: first value of the low index; last: first o_1 of the tile
+    uint32_t mid = 0;
     if constexpr (!LAST) {
-        const uint64_t chunks = 1ull << (P.below - LOGE); // column chunks per hi value
-        const uint64_t hi = tile / chunks;
-        rest0 = (tile % chunks) << LOGE;
+        const uint32_t chunk_bits = P.below - LOGE; // log2(column chunks per hi value)
+        const uint32_t hi = tile >> chunk_bits;
+        rest0 = (tile & ((1u << chunk_bits) - 1u)) << LOGE;
         in_base = (hi << (g + P.below)) + rest0;
     } else {
-        const uint64_t o1_chunks = 1ull << (P.g1 - LOGE);
-        rest0 = (tile % o1_chunks) << LOGE;
-        mid = tile / o1_chunks;
+        const uint32_t o1_bits = P.g1 - LOGE;
+        rest0 = (tile & ((1u << o1_bits) - 1u)) << LOGE;
+        mid = tile >> o1_bits;
     }
 
     fr x[E];
@@ -288,14 +326,14 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
 #pragma unroll
             for (int j = 0; j < E; ++j) {
                 const uint32_t row = (uint32_t)j * rows8 + q;
-                const uint64_t a = in_base + ((uint64_t)row << P.below) + col;
+                const uint32_t a = in_base + (row << P.below) + col;
                 x[j] = fe_load<FrParams>(P.src + a);
-                const uint64_t at = insert_bits(a, P.rk_pos, P.rk_bits, P.rk_val); // true coefficient index
+                const uint32_t at = (uint32_t)insert_bits(a, P.rk_pos, P.rk_bits, P.rk_val); // true coefficient index
                 if (P.pro_full != nullptr) {
                     if (at < P.pro_size) x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.pro_full + at));
                 } else if (P.pro_lo != nullptr && at < P.pro_size) {
                     fr s = fe_mul(fe_load_nc<FrParams>(P.pro_hi + (at >> P.pro_split)),
-                                  fe_load_nc<FrParams>(P.pro_lo + (at & ((1ull << P.pro_split) - 1))));
+                                  fe_load_nc<FrParams>(P.pro_lo + (at & ((1u << P.pro_split) - 1u))));
                     x[j] = fe_mul(x[j], s);
                 }
             }
@@ -308,14 +346,14 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
             for (uint32_t it = 0; it < (uint32_t)E; ++it) {
                 const uint32_t idx = it * R + tau;   // [0, E R): column-major
                 const uint32_t c = idx >> g, row = idx & (R - 1);
-                const uint64_t hi_idx = ((rest0 + c) << mid_bits_total) | mid;
-                uint64_t a;
+                const uint32_t hi_idx = ((rest0 + c) << mid_bits_total) | mid;
+                uint32_t a;
                 if (P.rk_bits == 0) {
                     a = (hi_idx << g) + row;
                 } else {
                     // after the all-to-all the row is split by source rank: chunk s holds i_P = (s, low)
                     const uint32_t src_rank = row >> P.split_low, low = row & ((1u << P.split_low) - 1);
-                    a = ((uint64_t)src_rank << P.chunk_log) + (hi_idx << P.split_low) + low;
+                    a = (src_rank << P.chunk_log) + (hi_idx << P.split_low) + low;
                 }
                 fr v = fe_load<FrParams>(P.src + a);
                 smem_store(sm, half_stride, sm_idx<LOGE>(tile_local, R, row, c), v);
@@ -349,8 +387,11 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
             }
         }
         const uint32_t lo_part = q & ((1u << w0) - 1);
+        if constexpr (TMA_TW) {
+            if (first) tw_bar.wait(std::move(tw_token)); // the twiddles have landed (every thread waits: inactive ones too)
+        }
         if (active) {
-            radix_round<LOGE>(x, g, w0, (uint32_t)b_hi, lo_part, P.stage_tw);
+            radix_round<LOGE, TMA_TW>(x, g, w0, (uint32_t)b_hi, lo_part, stage_tw);
         }
         b_hi = (int)w0 - 1;
         if (b_hi < 0) {
@@ -378,49 +419,49 @@ __global__ void __launch_bounds__(NTT_THREADS, NttGeom<LOGE>::MIN_CTAS) k_ntt_pa
         for (int j = 0; j < E; ++j) {
             const uint32_t rho = (q << LOGE) | (uint32_t)j;
             const uint32_t o = bitrev(rho, g);
-            const uint64_t rest = insert_bits(rest0 + col, P.rk_pos, P.rk_bits, P.rk_val);
-            // inter-pass twiddle w_N^( 2^above * o * rest )
-            uint64_t e = (((uint64_t)o * rest) << P.above) & (N - 1);
+            const uint32_t rest = (uint32_t)insert_bits(rest0 + col, P.rk_pos, P.rk_bits, P.rk_val);
+            // inter-pass twiddle w_N^( 2^above * o * rest ); (x << above) mod N == (x mod (N >> above)) << above
+            uint32_t e = ((o * rest) & (Nmask >> P.above)) << P.above;
             if (P.tw_scaled != nullptr) {
                 if (P.inverse) {
-                    e = (N - e) & (N - 1);
+                    e = (Nmask + 1u - e) & Nmask;
                 }
                 x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.tw_scaled + e));
             } else if (e != 0) {
                 if (P.inverse) {
-                    e = N - e;
+                    e = Nmask + 1u - e;
                 }
                 x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.tw_big + e));
             }
-            const uint64_t a = in_base + ((uint64_t)o << P.below) + col;
+            const uint32_t a = in_base + (o << P.below) + col;
             fe_store(P.dst + a, x[j]);
         }
     } else {
         // natural-order output index: o_1 + sum_q o_q * 2^(bits before q) + o_P * 2^above
-        uint64_t obase = ((uint64_t)P.rk_val << P.g1) | (rest0 + col); // true o_1 (this rank owns its top rk_bits)
+        uint32_t obase = (P.rk_val << P.g1) | (rest0 + col); // true o_1 (this rank owns its top rk_bits)
         if (P.rk_bits == 0) obase = rest0 + col;
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
             if ((uint32_t)d < P.num_mid) {
-                const uint64_t dig = (mid >> P.mid_src_shift[d]) & ((1ull << P.mid_bits[d]) - 1);
+                const uint32_t dig = (mid >> P.mid_src_shift[d]) & ((1u << P.mid_bits[d]) - 1u);
                 obase |= dig << P.mid_dst_shift[d];
             }
         }
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const uint32_t rho = (q << LOGE) | (uint32_t)j;
-            const uint64_t o = obase | ((uint64_t)bitrev(rho, g) << P.above);
+            const uint32_t o = obase | (bitrev(rho, g) << P.above);
             if (P.epi_mode == 1) {
                 x[j] = fe_mul(x[j], P.epi_const);
             } else if (P.epi_mode == 2) {
                 fr s = fe_mul(fe_load_nc<FrParams>(P.epi_hi + (o >> P.epi_split)),
-                              fe_load_nc<FrParams>(P.epi_lo + (o & ((1ull << P.epi_split) - 1))));
+                              fe_load_nc<FrParams>(P.epi_lo + (o & ((1u << P.epi_split) - 1u))));
                 x[j] = fe_mul(x[j], s);
             } else if (P.epi_mode == 3) {
                 x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.epi_full + o));
             }
-            const uint64_t ol = P.rk_bits ? squeeze_bits(o, P.g1, P.rk_bits) : o; // local slot of natural index o
-            fe_store(P.dst + ((ol << P.out_shift) + P.out_off), x[j]);
+            const uint32_t ol = P.rk_bits ? (uint32_t)squeeze_bits(o, P.g1, P.rk_bits) : o; // local slot of natural index o
+            fe_store(P.dst + (((size_t)ol << P.out_shift) + P.out_off), x[j]);
         }
     }
 }
@@ -821,6 +862,10 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<3>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, true, 3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES + NTT_TW_SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, false, 3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES + NTT_TW_SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<1>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<1>::SMEM_BYTES));
         ctx->ntt_attr_set = true;
@@ -833,6 +878,14 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         return v && *v ? (unsigned)atoi(v) : 0u;
     }();
     const unsigned loge = (loge_env >= 1 && loge_env <= 3) ? loge_env : (log_n <= 16 ? 1u : NTT_DEFAULT_LOGE);
+    static const bool tma_twiddles = [] {
+        const char* v = getenv("BBG_NTT_TMA_TWIDDLES"); // default on; 0 = read the stage twiddles through the read-only path
+        return !(v && *v == '0');
+    }();
+    static const bool e4_two_ctas = [] {
+        const char* v = getenv("BBG_NTT_E4_CTAS");
+        return v && *v == '2';
+    }();
 
     if (rb > 0 && (gb[num_passes - 1] < rb + 3 || gb[0] < rb + 3)) {
         set_last_error("ntt: too many ranks for this transform size");
@@ -928,6 +981,13 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         if (loge == 1) {
             if (last) k_ntt_pass<1, true><<<blocks, NTT_THREADS, NttGeom<1>::SMEM_BYTES, st>>>(pp);
             else k_ntt_pass<1, false><<<blocks, NTT_THREADS, NttGeom<1>::SMEM_BYTES, st>>>(pp);
+        } else if (loge == 2 && e4_two_ctas) {
+            // experiment knob (BBG_NTT_E4_CTAS=2): 128 registers, no spills, 4 instead of 6 warps per scheduler
+            if (last) k_ntt_pass<2, true, 2><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
+            else k_ntt_pass<2, false, 2><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
+        } else if (loge == 2 && tma_twiddles) {
+            if (last) k_ntt_pass<2, true, 3, true><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES + NTT_TW_SMEM_BYTES, st>>>(pp);
+            else k_ntt_pass<2, false, 3, true><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES + NTT_TW_SMEM_BYTES, st>>>(pp);
         } else if (loge == 2) {
             if (last) k_ntt_pass<2, true><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
             else k_ntt_pass<2, false><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
