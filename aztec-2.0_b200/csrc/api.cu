@@ -459,6 +459,19 @@ uint64_t bbg_kernel_launches(void) { return g_ctx ? g_ctx->launches : 0; }
 double bbg_last_device_ms(void) { return g_ctx ? g_ctx->last_kernel_ms : 0.0; }
 
 static_assert(BBG_NUM_PHASES == PH_COUNT, "include/bbg.h BBG_NUM_PHASES must cover every Phase");
+// totals of the host-pointer entry points since the library was loaded: for each of msm, ntt, srs, poly:
+// calls, H2D bytes, D2H bytes (12 values)
+int bbg_stats_totals(uint64_t* out12)
+{
+    if (!out12) return BBG_ERR_ARG;
+    for (int i = 0; i < 4; ++i) {
+        out12[3 * i] = g_stats.rows[i].calls;
+        out12[3 * i + 1] = g_stats.rows[i].bytes_h2d;
+        out12[3 * i + 2] = g_stats.rows[i].bytes_d2h;
+    }
+    return BBG_OK;
+}
+
 int bbg_profile(int enable)
 {
     GET_CTX();

@@ -97,7 +97,7 @@ struct StatScope {
     std::chrono::steady_clock::time_point t0;
     uint64_t h2d, d2h, launches0 = 0;
     StatScope(int which, Context* c, uint64_t h2d_, uint64_t d2h_)
-        : row(g_stats.enabled ? &g_stats.rows[which] : nullptr), ctx(c), h2d(h2d_), d2h(d2h_)
+        : row(&g_stats.rows[which]), ctx(c), h2d(h2d_), d2h(d2h_) // always accounted (a few adds); printing is what BBG_STATS gates
     {
         if (!row) return;
         launches0 = ctx->launches;

@@ -632,9 +632,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2) k_msm_pair_pass(const uint32_
 
 // One merge level: worker u folds slots [u*K + 1, (u+1)*K + 1) (worker 0 also takes slot 0), i.e. the
 // boundary falls between the two slots of one chunk so the typical (tail, next head) pair is never cut.
-__device__ __forceinline__ void merge_worker(const Slot* __restrict__ in, uint32_t n_in, uint32_t workers, uint32_t u,
+// A worker is a TEAM of four lanes (g1_team.cuh): the chain of up to MERGE_K - 1 additions per level is what this phase
+// costs, and there are far fewer workers than lanes.  All lanes of a team read the same slots and take the same branches;
+// lane 0 writes.
+__device__ __forceinline__ void merge_worker(const Team& tm, const Slot* __restrict__ in, uint32_t n_in, uint32_t workers, uint32_t u,
                                              xyzz_t* __restrict__ buckets, Slot* __restrict__ out, uint32_t* __restrict__ pending_out)
 {
+    const bool writer = tm.r == 0;
     const uint32_t lo = u == 0 ? 0 : u * MERGE_K + 1;
     uint32_t hi = (u + 1) * MERGE_K + 1;
     if (hi > n_in || u + 1 == workers) hi = n_in;
@@ -652,14 +656,14 @@ __device__ __forceinline__ void merge_worker(const Slot* __restrict__ in, uint32
             const bool cont_l = run_start == lo && lo > 0 && in[lo - 1].bucket == run_bucket;
             const bool cont_r = i == hi && hi < n_in && in[hi].bucket == run_bucket;
             if (!cont_l && !cont_r) {
-                xyzz_store(buckets + run_bucket, acc);
+                if (writer) xyzz_store(buckets + run_bucket, acc);
             } else {
                 if (cont_l) {
-                    slot_store(out_a, acc, run_bucket);
+                    if (writer) slot_store(out_a, acc, run_bucket);
                     a_set = true;
                 }
                 if (cont_r) {
-                    slot_store(out_b, cont_l ? xyzz_infinity() : acc, run_bucket);
+                    if (writer) slot_store(out_b, cont_l ? xyzz_infinity() : acc, run_bucket);
                     b_set = true;
                 }
             }
@@ -672,18 +676,20 @@ __device__ __forceinline__ void merge_worker(const Slot* __restrict__ in, uint32
                 run_start = i;
                 acc = x;
             } else {
-                xyzz_add(acc, x); // the one inlined add site of this kernel
+                xyzz_add_team(tm, acc, x); // the one inlined add site of this kernel
             }
         }
     }
-    if (!a_set) out_a->bucket = SLOT_NONE;
-    if (!b_set) out_b->bucket = SLOT_NONE;
-    if (a_set || b_set) {
-        atomicAdd(pending_out, 1u);
+    if (writer) {
+        if (!a_set) out_a->bucket = SLOT_NONE;
+        if (!b_set) out_b->bucket = SLOT_NONE;
+        if (a_set || b_set) {
+            atomicAdd(pending_out, 1u);
+        }
     }
 }
 
-// level 0: one worker per thread over the 2 * num_chunks slots the accumulation left
+// levels 0-2: one team per worker over the slots the level before left
 __global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
                                                     uint32_t n_in,
                                                     uint32_t workers,
@@ -693,13 +699,14 @@ __global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
                                                     uint32_t* __restrict__ pending_out)
 {
     if (__ldg(pending_in) == 0) {
-        return; // no bucket was cut by a chunk boundary
+        return; // nothing was left open
     }
-    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    const Team tm = team_of_lane();
+    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     if (u >= workers) {
-        return;
+        return; // team-uniform
     }
-    merge_worker(in, n_in, workers, u, buckets, out, pending_out);
+    merge_worker(tm, in, n_in, workers, u, buckets, out, pending_out);
 }
 
 // Levels 0-2 are ordinary grid-wide launches of k_msm_merge (each exits at once when the level before left nothing
@@ -707,10 +714,11 @@ __global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
 // equal -- is finished by ONE single-CTA launch that loops over the remaining levels with a block barrier in between
 // (level 3 has at most num_chunks / 256 workers).  Round 1 launched up to 14 levels one by one.
 static constexpr int MERGE_GRID_LEVELS = 3;
-static constexpr int MERGE_REST_THREADS = 512;
+static constexpr int MERGE_REST_THREADS = 256; // 64 teams
 __global__ void __launch_bounds__(MERGE_REST_THREADS) k_msm_merge_rest(Slot* __restrict__ slots, uint32_t n_in, uint32_t first_level,
                                                                         uint32_t* __restrict__ pending, xyzz_t* __restrict__ buckets)
 {
+    const Team tm = team_of_lane();
     Slot* in = slots;
     for (uint32_t level = first_level; level < 15; ++level) {
         if (*(volatile uint32_t*)(pending + level) == 0) {
@@ -718,8 +726,8 @@ __global__ void __launch_bounds__(MERGE_REST_THREADS) k_msm_merge_rest(Slot* __r
         }
         const uint32_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
         Slot* out = in + n_in;
-        for (uint32_t u = threadIdx.x; u < workers; u += MERGE_REST_THREADS) {
-            merge_worker(in, n_in, workers, u, buckets, out, pending + level + 1);
+        for (uint32_t u = threadIdx.x >> 2; u < workers; u += MERGE_REST_THREADS / 4) {
+            merge_worker(tm, in, n_in, workers, u, buckets, out, pending + level + 1);
         }
         __threadfence();
         __syncthreads();
@@ -1359,8 +1367,8 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
             const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
             Slot* out = in + n_in;
             if (level < MERGE_GRID_LEVELS) {
-                k_msm_merge<<<div_up(workers, 128), 128, 0, st>>>(in, (uint32_t)n_in, (uint32_t)workers, pending + level, buckets, out,
-                                                                 pending + level + 1);
+                k_msm_merge<<<div_up(workers * 4, 128), 128, 0, st>>>(in, (uint32_t)n_in, (uint32_t)workers, pending + level, buckets, out,
+                                                                     pending + level + 1);
                 ctx->launches += 1;
             } else {
                 k_msm_merge_rest<<<1, MERGE_REST_THREADS, 0, st>>>(in, (uint32_t)n_in, level, pending, buckets);

@@ -37,7 +37,7 @@ EXPORTS = [
     "bbg_pippenger_unsafe_batch", "bbg_pippenger_unsafe_batch_dev", "bbg_pippenger_batch",
     "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_ntt_ex", "bbg_wire_coset_fft", "bbg_turbo_quotient",
     "bbg_permutation_quotient", "bbg_divide_by_pseudo_vanishing_polynomial", "bbg_compute_lagrange_polynomial_fft",
-    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_wire_ifft", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
+    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_wire_ifft", "bbg_stats_totals", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
 ]
 
 
@@ -121,6 +121,7 @@ lib.bbg_permutation_grand_product.argtypes = [_vp, _vp, ctypes.c_uint, _sz, _vp,
 lib.bbg_evaluate.argtypes = [_vp, _sz, _vp, _vp]
 lib.bbg_compute_opening_polynomial.argtypes = [_vp, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint]
 lib.bbg_poly_write.argtypes = [_vp, _sz, _vp, _sz]
+lib.bbg_stats_totals.argtypes = [_vp]
 lib.bbg_wire_ifft.argtypes = [_vp, _sz, _vp]
 lib.bbg_evaluate_batch.argtypes = [_vp, _vp, _sz, _vp, _vp]
 lib.bbg_linear_combination.argtypes = [_vp, _vp, _vp, _vp, _sz, _sz, ctypes.c_uint]
@@ -347,6 +348,12 @@ def resident_mode(enable):
     if enable < 0:
         return rc
     _check(rc)
+
+
+def stats_totals():
+    out = (ctypes.c_uint64 * 12)()
+    _check(lib.bbg_stats_totals(ctypes.cast(out, _vp)))
+    return {name: {"calls": int(out[3 * i]), "h2d": int(out[3 * i + 1]), "d2h": int(out[3 * i + 2])} for i, name in enumerate(("msm", "ntt", "srs", "poly"))}
 
 
 def resident_stats():

@@ -849,9 +849,8 @@ def prover_record(reps_gpu=6, reps_cpu=3):
         rec = {"construct_proof_ms_all": [round(t * 1e3, 3) for t in times], "construct_proof_ms": steady[len(steady) // 2] * 1e3,
                "keygen_s": d["keygen_s"], "keygen_warm_s": d.get("keygen_warm_s"), "cuda_init_s": d.get("cuda_init_s"), "verified": d["verified"],
                "kernel_launches": d["gpu_kernel_launches"]}
-        if stats:
-            n_proofs = len(times)
-            rec["pcie_bytes_whole_run"] = {k: {"h2d": v["h2d_bytes"], "d2h": v["d2h_bytes"], "calls": v["calls"]} for k, v in stats.items()}
+        if "h2d_bytes" in d["proofs"][-1] and name != "js_prover_cpu":
+            rec["pcie_bytes_per_proof"] = {"h2d": d["proofs"][-1]["h2d_bytes"], "d2h": d["proofs"][-1]["d2h_bytes"]}
         if name == "js_prover_cpu":
             ref_proof = d["first_proof"]
         else:

@@ -48,6 +48,10 @@ int bbg_device_count(void);
 uint64_t bbg_kernel_launches(void);    /* kernels this library has launched so far (bench.py reports it) */
 double bbg_last_device_ms(void);       /* CUDA-event time of the kernels of the last host-pointer call */
 
+/* Totals of the host-pointer entry points since the library was loaded -- calls, H2D bytes, D2H bytes for each of
+ * msm, ntt, srs, poly (12 values).  BBG_STATS=1 prints the same (plus wall / kernel time) at exit. */
+int bbg_stats_totals(uint64_t* out12);
+
 /* Per-phase device timing of the LAST compute call (CUDA events on the launching stream; measurement aid
  * for bench.py, no reference counterpart).  Phases: 0 msm digits+histogram, 1 scan, 2 scatter, 3 pairwise affine
  * passes (optional path), 4 bucket accumulate, 5 slot merge, 6 bucket reduce, 7 window combine, 8 ntt tables,

@@ -88,6 +88,19 @@ int main(int argc, char** argv)
     init_verification_key(std::make_unique<waffle::FileReferenceStringFactory>(srs));
     double t_keys_warm = now() - t0;
 
+    // PCIe bytes per proof, when libbbg is underneath (bbg_stats_totals: calls / H2D / D2H of msm, ntt, srs, poly)
+    typedef int (*totals_fn)(uint64_t*);
+    totals_fn totals = reinterpret_cast<totals_fn>(dlsym(RTLD_DEFAULT, "bbg_stats_totals"));
+    auto pcie_now = [&](uint64_t& h2d, uint64_t& d2h) {
+        h2d = d2h = 0;
+        if (!totals) return;
+        uint64_t t[12];
+        totals(t);
+        for (int i = 0; i < 4; ++i) {
+            h2d += t[3 * i + 1];
+            d2h += t[3 * i + 2];
+        }
+    };
     std::vector<uint8_t> proof, first_proof;
     std::string times;
     bool ok = true;
@@ -97,11 +110,14 @@ int main(int argc, char** argv)
         double t1 = now();
         auto prover = new_join_split_prover(tx); // circuit + witness (CPU in both binaries)
         double t2 = now();
+        uint64_t h0, d0, h1, d1;
+        pcie_now(h0, d0);
         proof = prover.construct_proof().proof_data; // the part the hot path accelerates
         double t3 = now();
+        pcie_now(h1, d1);
         gates = prover.get_circuit_size();
         times += (r ? ", " : "") + std::string("{\"witness_s\": ") + std::to_string(t2 - t1) + ", \"construct_proof_s\": " +
-                 std::to_string(t3 - t2) + "}";
+                 std::to_string(t3 - t2) + ", \"h2d_bytes\": " + std::to_string(h1 - h0) + ", \"d2h_bytes\": " + std::to_string(d1 - d0) + "}";
         ok = ok && verify_proof(waffle::plonk_proof{ proof });
         if (r == 0) first_proof = proof;
     }

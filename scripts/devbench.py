@@ -6,7 +6,7 @@ from oracle import pyoracle as po
 
 def main():
     bbg.init(0)
-    logs = [int(x) for x in (sys.argv[1].split(',') if len(sys.argv) > 1 else ['16', '20'])]
+    logs = [int(x) for x in (sys.argv[1].split(',') if len(sys.argv) > 1 else ['16', '20']) if x]
     ntt_logs = [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else ['16', '20', '22', '24']) if x]
     srs_dir = po.REF_SRS_DIR if os.path.exists(os.path.join(po.REF_SRS_DIR, 'transcript00.dat')) else inputs.SRS_MINI_DIR
     nmax = 1 << max(logs) if logs else 0

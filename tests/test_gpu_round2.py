@@ -263,3 +263,22 @@ def test_field_op_dev_reduce(bbg, orc):
     out = bbg.field_op_dev(po.FR, 7, d)
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().view(np.uint64), orc.reduce(po.FR, a))
+
+
+def test_stats_totals_count_pcie_bytes(bbg):
+    """bbg_stats_totals: what the prover harness differences to report PCIe bytes per proof"""
+    x = inputs.fr_elements(970, 1 << 12)
+    t0 = bbg.stats_totals()
+    bbg.fft(x)
+    t1 = bbg.stats_totals()
+    assert t1["ntt"]["calls"] == t0["ntt"]["calls"] + 1
+    assert t1["ntt"]["h2d"] - t0["ntt"]["h2d"] == x.nbytes and t1["ntt"]["d2h"] - t0["ntt"]["d2h"] == x.nbytes
+    bbg.resident_mode(True)
+    try:
+        bbg.ifft(x)  # uploads once, mirror kept
+        t2 = bbg.stats_totals()
+        bbg.fft(x)   # mirror hit: nothing goes up
+        t3 = bbg.stats_totals()
+        assert t3["ntt"]["h2d"] == t2["ntt"]["h2d"] and t3["ntt"]["d2h"] - t2["ntt"]["d2h"] == x.nbytes
+    finally:
+        bbg.resident_mode(False)
