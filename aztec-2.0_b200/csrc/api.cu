@@ -1124,6 +1124,83 @@ int bbg_ntt_dist_dev(const void* d_src, void* d_dst, size_t n, int kind, size_t 
     return ntt_device(ctx, d_src, d_dst, lg, inverse, pro, epi, 0, 0, (cudaStream_t)stream, dist);
 }
 
+// Phase 0 of the multi-GPU NTT with the exchange FUSED into its last pass: the intermediate is written straight into the
+// receive buffers of the owning ranks over NVLink peer memory (peer_recv[r] = rank r's buffer of n / world elements, opened
+// with bbg_peer_buffer_open; peer_recv[rank] = this rank's own).  d_work: n / world elements of local scratch for the
+// earlier passes.  world <= 8.  The caller must make sure (a stream-ordered all-reduce is enough) that every rank has finished
+// this call before any rank runs phase 1 on its receive buffer.
+int bbg_ntt_dist_fused_dev(const void* d_src, void* d_work, void* const* peer_recv, size_t n, int kind, size_t generator_size,
+                           const void* constant, int rank, int world, void* stream)
+{
+    GET_CTX();
+    StreamScope order(ctx, (cudaStream_t)stream);
+    unsigned lg;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    unsigned ip, op;
+    if ((rc = bbg_ntt_dist_layout(n, world, &ip, &op))) return rc;
+    if (rank < 0 || rank >= world || world < 2 || world > 8 || peer_recv == nullptr) {
+        set_last_error("ntt_dist_fused: 2..8 ranks and a table of peer receive buffers");
+        return BBG_ERR_ARG;
+    }
+    bool inverse;
+    NttScale pro, epi;
+    if ((rc = ntt_kind_params(kind, lg, generator_size, constant, inverse, pro, epi))) return rc;
+    NttDist dist;
+    dist.rank = (unsigned)rank;
+    dist.phase = 0;
+    dist.peer_recv = peer_recv;
+    while ((1 << dist.rank_bits) < world) ++dist.rank_bits;
+    return ntt_device(ctx, d_src, d_work, lg, inverse, pro, epi, 0, 0, (cudaStream_t)stream, dist);
+}
+
+// ---- peer-mapped buffers (CUDA IPC): memory another rank's kernels can store into over NVLink
+int bbg_peer_buffer_alloc(size_t bytes, void** d_ptr, void* ipc_handle64)
+{
+    GET_CTX();
+    if (!d_ptr || !ipc_handle64 || bytes == 0) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C-ABI passes IPC handles as 64 opaque bytes");
+    void* p = nullptr;
+    BBG_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_last_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+        return BBG_ERR_CUDA;
+    }
+    memcpy(ipc_handle64, &h, 64);
+    *d_ptr = p;
+    return BBG_OK;
+}
+int bbg_peer_buffer_open(const void* ipc_handle64, void** d_ptr)
+{
+    GET_CTX();
+    if (!d_ptr || !ipc_handle64) {
+        set_last_error("null argument");
+        return BBG_ERR_ARG;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, 64);
+    BBG_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BBG_OK;
+}
+int bbg_peer_buffer_close(void* d_ptr)
+{
+    GET_CTX();
+    if (d_ptr) BBG_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return BBG_OK;
+}
+int bbg_peer_buffer_free(void* d_ptr)
+{
+    GET_CTX();
+    if (d_ptr) BBG_CUDA(cudaFree(d_ptr));
+    return BBG_OK;
+}
+
 static int coset_fft_ext_device(Context* ctx, void* d_coeffs, unsigned lg, size_t ext, cudaStream_t st)
 {
     unsigned lg_ext = 0;

@@ -76,6 +76,7 @@ struct NttDist {
     unsigned rank_bits = 0; // log2(number of ranks); 0 = single GPU
     unsigned rank = 0;
     int phase = 0;          // 0: every pass but the last (before the all-to-all); 1: the last pass (after it)
+    void* const* peer_recv = nullptr; // phase 0, fused exchange: receive buffer of every rank (peer-mapped); null = local store + NCCL
 };
 int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, bool inverse, const NttScale& pro, const NttScale& epi,
                unsigned out_shift, unsigned out_off, cudaStream_t st, const NttDist& dist = NttDist());

@@ -112,6 +112,12 @@ struct PassParams {
     uint32_t mid_bits_total; // last pass: total width of digits 2..P-1
     uint32_t split_low;      // last pass, after the all-to-all: a row is rk_bits source-rank chunks of 2^split_low elements,
     uint32_t chunk_log;      //   chunk s starting at s << chunk_log
+    // Fused exchange (multi-GPU, the pass before the last): instead of writing the intermediate locally and handing it
+    // to an NCCL all-to-all, every element is stored straight into the receive buffer of the rank that owns its chunk,
+    // over NVLink peer memory: element a of the local intermediate belongs to chunk a >> chunk_log, and lands at slot
+    // (rk_val << chunk_log) + (a & chunk mask) of that rank's buffer -- exactly where the all-to-all would have put it.
+    uint32_t peer_on;
+    fr* peer_dst[8];
 };
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return __brev(x) >> (32 - bits); }
@@ -434,7 +440,12 @@ __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams
                 x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.tw_big + e));
             }
             const uint32_t a = in_base + (o << P.below) + col;
-            fe_store(P.dst + a, x[j]);
+            if (P.peer_on) {
+                const uint32_t owner = a >> P.chunk_log;
+                fe_store(P.peer_dst[owner] + ((P.rk_val << P.chunk_log) | (a & ((1u << P.chunk_log) - 1u))), x[j]);
+            } else {
+                fe_store(P.dst + a, x[j]);
+            }
         }
     } else {
         // natural-order output index: o_1 + sum_q o_q * 2^(bits before q) + o_P * 2^above
@@ -944,6 +955,12 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
                 pp.mid_dst_shift[d] = dst_shift;
                 dst_shift += bits;
             }
+        }
+        pp.peer_on = 0;
+        for (auto& q : pp.peer_dst) q = nullptr;
+        if (rb > 0 && dist.peer_recv != nullptr && dist.phase == 0 && p + 2 == num_passes) {
+            pp.peer_on = 1;
+            for (unsigned r = 0; r < (1u << rb); ++r) pp.peer_dst[r] = (fr*)dist.peer_recv[r];
         }
         pp.pro_lo = (p == 0) ? pro_lo : nullptr;
         pp.pro_hi = (p == 0) ? pro_hi : nullptr;

@@ -13,6 +13,7 @@
 //                                                                                widgets/transition_widgets/transition_widget.hpp:293-307
 //   polynomial_arithmetic::divide_by_pseudo_vanishing_polynomial                 bb/polynomials/polynomial_arithmetic.cpp:628-725
 //   polynomial_arithmetic::evaluate                                              bb/polynomials/polynomial_arithmetic.cpp:507-538
+//   polynomial_arithmetic::compute_lagrange_polynomial_fft  (key generation)     bb/polynomials/polynomial_arithmetic.cpp:546-626
 //   KateCommitmentScheme<{turbo,unrolled_turbo}_settings>::batch_open            commitment_scheme/kate_commitment_scheme.cpp:133-237
 //   KateCommitmentScheme<{turbo,unrolled_turbo}_settings>::add_opening_evaluations_to_transcript   ... :373-436
 //
@@ -306,6 +307,12 @@ void divide_by_pseudo_vanishing_polynomial(fr* coeffs, const evaluation_domain& 
 // ------------------------------------------------------------------------------------------------------------------
 namespace barretenberg {
 namespace polynomial_arithmetic {
+void compute_lagrange_polynomial_fft(fr* l_1_coefficients, const evaluation_domain& src_domain, const evaluation_domain& target_domain)
+{
+    Trace trace("compute_lagrange_polynomial_fft");
+    check(bbg_compute_lagrange_polynomial_fft(l_1_coefficients, src_domain.size, target_domain.size));
+}
+
 fr evaluate(const fr* coeffs, const fr& z, const size_t n)
 {
     Trace trace("evaluate");

@@ -37,7 +37,8 @@ EXPORTS = [
     "bbg_pippenger_unsafe_batch", "bbg_pippenger_unsafe_batch_dev", "bbg_pippenger_batch",
     "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_ntt_ex", "bbg_wire_coset_fft", "bbg_turbo_quotient",
     "bbg_permutation_quotient", "bbg_divide_by_pseudo_vanishing_polynomial", "bbg_compute_lagrange_polynomial_fft",
-    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_wire_ifft", "bbg_stats_totals", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
+    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_wire_ifft", "bbg_stats_totals", "bbg_ntt_dist_fused_dev",
+    "bbg_peer_buffer_alloc", "bbg_peer_buffer_open", "bbg_peer_buffer_close", "bbg_peer_buffer_free", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
 ]
 
 
@@ -122,6 +123,11 @@ lib.bbg_evaluate.argtypes = [_vp, _sz, _vp, _vp]
 lib.bbg_compute_opening_polynomial.argtypes = [_vp, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint]
 lib.bbg_poly_write.argtypes = [_vp, _sz, _vp, _sz]
 lib.bbg_stats_totals.argtypes = [_vp]
+lib.bbg_ntt_dist_fused_dev.argtypes = [_vp, _vp, _vp, _sz, _int, _sz, _vp, _int, _int, _vp]
+lib.bbg_peer_buffer_alloc.argtypes = [_sz, _vp, _vp]
+lib.bbg_peer_buffer_open.argtypes = [_vp, _vp]
+lib.bbg_peer_buffer_close.argtypes = [_vp]
+lib.bbg_peer_buffer_free.argtypes = [_vp]
 lib.bbg_wire_ifft.argtypes = [_vp, _sz, _vp]
 lib.bbg_evaluate_batch.argtypes = [_vp, _vp, _sz, _vp, _vp]
 lib.bbg_linear_combination.argtypes = [_vp, _vp, _vp, _vp, _sz, _sz, ctypes.c_uint]
@@ -490,6 +496,45 @@ def ntt_dist_phase(src, dst, n, kind, rank, world, phase, generator_size=0, cons
     """One phase of the multi-GPU NTT on torch CUDA tensors (include/bbg.h bbg_ntt_dist_dev)."""
     k = None if constant is None else _np(constant, 4)
     _check(lib.bbg_ntt_dist_dev(src.data_ptr(), dst.data_ptr(), n, kind, generator_size, None if k is None else k.ctypes.data,
+                                rank, world, phase, _stream_ptr(stream)))
+    return dst
+
+
+def peer_buffer_alloc(nbytes):
+    """(device pointer, 64-byte IPC handle) of a buffer other ranks can map (bbg_peer_buffer_alloc)"""
+    ptr = ctypes.c_void_p(0)
+    handle = (ctypes.c_uint8 * 64)()
+    _check(lib.bbg_peer_buffer_alloc(nbytes, ctypes.cast(ctypes.pointer(ptr), _vp), ctypes.cast(handle, _vp)))
+    return int(ptr.value), bytes(handle)
+
+
+def peer_buffer_open(handle):
+    ptr = ctypes.c_void_p(0)
+    buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+    _check(lib.bbg_peer_buffer_open(ctypes.cast(buf, _vp), ctypes.cast(ctypes.pointer(ptr), _vp)))
+    return int(ptr.value)
+
+
+def peer_buffer_close(ptr):
+    _check(lib.bbg_peer_buffer_close(ptr))
+
+
+def peer_buffer_free(ptr):
+    _check(lib.bbg_peer_buffer_free(ptr))
+
+
+def ntt_dist_fused_phase0(src, work, peer_ptrs, n, kind, rank, world, generator_size=0, constant=None, stream=None):
+    """phase 0 with the exchange fused into its last pass (bbg_ntt_dist_fused_dev); peer_ptrs: `world` raw device pointers"""
+    k = None if constant is None else _np(constant, 4)
+    tab = (ctypes.c_void_p * world)(*peer_ptrs)
+    _check(lib.bbg_ntt_dist_fused_dev(src.data_ptr(), work.data_ptr(), ctypes.cast(tab, _vp), n, kind, generator_size,
+                                      None if k is None else k.ctypes.data, rank, world, _stream_ptr(stream)))
+
+
+def ntt_dist_phase_raw(src_ptr, dst, n, kind, rank, world, phase, generator_size=0, constant=None, stream=None):
+    """bbg_ntt_dist_dev with a raw device pointer as the source (a peer-mapped receive buffer)"""
+    k = None if constant is None else _np(constant, 4)
+    _check(lib.bbg_ntt_dist_dev(src_ptr, dst.data_ptr(), n, kind, generator_size, None if k is None else k.ctypes.data,
                                 rank, world, phase, _stream_ptr(stream)))
     return dst
 

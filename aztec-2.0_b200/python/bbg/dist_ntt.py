@@ -44,6 +44,59 @@ def ntt_sharded(bbg, local_in, n, kind, rank, world, generator_size=0, constant=
     return out
 
 
+class FusedExchange:
+    """Peer-mapped receive buffers for ntt_sharded_fused: two per rank (alternated between consecutive transforms so
+    that a peer's stores for transform k + 1 never land in the buffer this rank is still reading for transform k),
+    IPC handles exchanged once through torch.distributed."""
+
+    def __init__(self, bbg, n, rank, world, group=None):
+        import torch
+        import torch.distributed as dist
+        self.bbg, self.n, self.rank, self.world, self.group = bbg, n, rank, world, group
+        self.m = n // world
+        self.own, self.peers = [], []
+        for _ in range(2):
+            ptr, handle = bbg.peer_buffer_alloc(self.m * 32)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            ptrs = [ptr if r == rank else bbg.peer_buffer_open(handles[r]) for r in range(world)]
+            self.own.append(ptr)
+            self.peers.append(ptrs)
+        self.turn = 0
+        self.token = torch.zeros(1, dtype=torch.float32, device="cuda")
+        dist.barrier(group=group)
+
+    def close(self):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for b in range(2):
+            for r in range(self.world):
+                if r != self.rank:
+                    self.bbg.peer_buffer_close(self.peers[b][r])
+        dist.barrier(group=self.group)
+        for b in range(2):
+            self.bbg.peer_buffer_free(self.own[b])
+
+
+def ntt_sharded_fused(bbg, local_in, n, kind, rank, world, xch, generator_size=0, constant=None):
+    """ntt_sharded with the all-to-all FUSED into the pass before it: that pass stores its results straight into the
+    owners' receive buffers over NVLink peer memory (bbg_ntt_dist_fused_dev), so the transfer overlaps the pass's
+    arithmetic and no NCCL all-to-all runs.  The only collective left is a one-word all-reduce that orders phase 1 after
+    every rank's stores (stream-ordered; the host does not wait).  Same layouts and bit-exact results as ntt_sharded."""
+    import torch
+    import torch.distributed as dist
+    b = xch.turn
+    xch.turn ^= 1
+    work = torch.empty_like(local_in)
+    bbg.ntt_dist_fused_phase0(local_in, work, xch.peers[b], n, kind, rank, world, generator_size, constant)
+    dist.all_reduce(xch.token, group=xch.group)  # every rank's peer stores are complete when this completes
+    out = torch.empty_like(local_in)
+    bbg.ntt_dist_phase_raw(xch.own[b], out, n, kind, rank, world, 1, generator_size, constant)
+    return out
+
+
 def ntt_sharded_natural(bbg, block_in, n, kind, rank, world, generator_size=0, constant=None, group=None, phase_fn=None, layout=None):
     """SURVEY.md 8e contract: rank r holds the NATURAL contiguous block x[r n/W, (r+1) n/W) and ends with the natural
     block X[r n/W, (r+1) n/W).  The four-step core wants its input sliced by index bits [in_pos, in_pos + k) and leaves its

@@ -185,6 +185,22 @@ int bbg_ntt_dist_dev(const void* d_src, void* d_dst, size_t n, int kind, size_t 
 #define BBG_KEEP_IF_AHEAD 2u
 int bbg_ntt_ex(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant, unsigned flags);
 
+/* The same with the exchange FUSED into the pass before it: phase 0's last pass stores every element straight into the
+ * receive buffer of the rank that owns its chunk, over NVLink peer memory, at the slot the all-to-all would have put it --
+ * the transfer overlaps the pass's arithmetic tile by tile and no NCCL all-to-all runs.  peer_recv: `world` device pointers
+ * (<= 8), peer_recv[r] = rank r's receive buffer of n / world elements mapped into this process (bbg_peer_buffer_open),
+ * peer_recv[rank] = this rank's own (bbg_peer_buffer_alloc); d_work: n / world elements of local scratch.  Before phase 1
+ * (bbg_ntt_dist_dev(..., phase = 1) on the own receive buffer) every rank must have finished this call: a stream-ordered
+ * all-reduce of one word is enough.  Alternate two receive buffers when transforms follow each other back to back. */
+int bbg_ntt_dist_fused_dev(const void* d_src, void* d_work, void* const* peer_recv, size_t n, int kind, size_t generator_size,
+                           const void* constant, int rank, int world, void* stream);
+/* Peer-mapped device buffers (CUDA IPC, one process per GPU): alloc returns the pointer and a 64-byte handle to send to
+ * the other ranks (any transport); open maps another rank's buffer into this process (lazy peer access over NVLink). */
+int bbg_peer_buffer_alloc(size_t bytes, void** d_ptr, void* ipc_handle64);
+int bbg_peer_buffer_open(const void* ipc_handle64, void** d_ptr);
+int bbg_peer_buffer_close(void* d_ptr);
+int bbg_peer_buffer_free(void* d_ptr);
+
 /* coset_fft(coeffs, small_domain, large_domain, domain_extension) (polynomial_arithmetic.cpp:401-456):
  * coeffs holds ext*n elements, the first n are the input; output interleaved out[ext*i + k]. */
 int bbg_coset_fft_ext(void* coeffs, size_t n, size_t domain_extension);
