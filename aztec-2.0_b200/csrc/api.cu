@@ -55,6 +55,13 @@ static int create_context(int device)
     BBG_CUDA(cudaEventCreate(&c->ev_b));
     BBG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (auto& e : c->ev_join) BBG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        int prio_low = 0, prio_high = 0;
+        BBG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+        for (auto& a : c->part_stream) BBG_CUDA(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, prio_high));
+        BBG_CUDA(cudaEventCreateWithFlags(&c->ev_part_fork, cudaEventDisableTiming));
+        for (auto& e : c->ev_part_join) BBG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     BBG_CUDA(cudaEventCreateWithFlags(&c->last_use, cudaEventDisableTiming));
     g_ctx = c;
     return BBG_OK;
@@ -438,6 +445,9 @@ void bbg_shutdown(void)
     cudaEventDestroy(g_ctx->ev_b);
     cudaEventDestroy(g_ctx->ev_fork);
     for (auto& e : g_ctx->ev_join) cudaEventDestroy(e);
+    cudaEventDestroy(g_ctx->ev_part_fork);
+    for (auto& e : g_ctx->ev_part_join) cudaEventDestroy(e);
+    for (auto& a : g_ctx->part_stream) cudaStreamDestroy(a);
     cudaEventDestroy(g_ctx->last_use);
     cudaStreamDestroy(g_ctx->stream);
     cudaStreamDestroy(g_ctx->copy_stream);
@@ -795,7 +805,7 @@ static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, 
             if ((rc = ws.result.reserve(96))) return rc;
             d_out = ws.result.p;
         }
-        if ((rc = msm_device(ctx, ws, d_sc, range, o->d_points, 1, o->lv, from, d_out, s))) return rc;
+        if ((rc = msm_device(ctx, ws, d_sc, range, o->d_points, 1, o->lv, from, d_out, s, nullptr, /*allow_parts=*/used == 1))) return rc;
         if (!device_results) BBG_CUDA(cudaMemcpyAsync((char*)ctx->pinned + i * 96, d_out, 96, cudaMemcpyDeviceToHost, s));
     }
     if (stat.row) stat.row->bytes_h2d += h2d;

@@ -101,6 +101,11 @@ struct Context {
     cudaEvent_t ev_piece[8] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[BATCH_WAYS - 1] = {};
+    // a single large MSM is cut into bucket ranges ("parts") whose accumulate -> merge -> reduce chains run on these
+    // high-priority streams, so that the latency-bound tail of one part runs under the accumulation of the next (msm.cu)
+    static constexpr int MSM_MAX_PARTS = 4;
+    cudaStream_t part_stream[MSM_MAX_PARTS - 1] = {};
+    cudaEvent_t ev_part_fork = nullptr, ev_part_join[MSM_MAX_PARTS - 1] = {};
     // Cross-stream ordering of the shared workspaces and cached tables: every call records `last_use` on its stream when
     // it has queued its work, and a call on a DIFFERENT stream first waits for it (StreamScope in internal.hpp).  Calls on
     // different streams therefore serialise on the device; they never race on the workspaces.

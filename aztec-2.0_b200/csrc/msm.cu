@@ -287,6 +287,8 @@ template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS, 4) k_msm_accumulate(const uint32_t* __restrict__ sorted,
                                                                    const uint32_t* __restrict__ offsets, // G+1
                                                                    uint32_t G,
+                                                                   uint32_t g_lo, // this launch takes the entries of buckets [g_lo, g_hi)
+                                                                   uint32_t g_hi,
                                                                    uint32_t chunk,
                                                                    uint32_t num_chunks,
                                                                    const affine_t* __restrict__ points,
@@ -301,8 +303,8 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) k_msm_accumulate(const uint32_
     }
     Slot* slot_a = slots + 2 * (size_t)t;
     Slot* slot_b = slot_a + 1;
-    const uint32_t total = __ldg(offsets + G); // number of non-zero digits, produced by the scan
-    const uint64_t start64 = (uint64_t)t * chunk;
+    const uint32_t total = __ldg(offsets + g_hi); // end of the range's entries (g_hi = G: the number of non-zero digits)
+    const uint64_t start64 = (uint64_t)__ldg(offsets + g_lo) + (uint64_t)t * chunk;
     if (start64 >= total) {
         slot_a->bucket = SLOT_NONE;
         slot_b->bucket = SLOT_NONE;
@@ -906,8 +908,12 @@ __global__ void __launch_bounds__(TREE_THREADS) k_msm_tree_sum(const xyzz_t* __r
 // 6. per set: V = R_0 + ell_0 (R_1 + ell_1 (R_2 + ...)) (one team per set), then
 //    result = sum_r 2^(c r) * V[r] (team 0), XYZZ -> Jacobian.  level_sums[level * S + set].
 static constexpr int FINISH_THREADS = 256; // 64 teams; more bucket sets than that are taken in turns
+//    Part of a bucket set (weight_offset != 0): the buckets handed in are [weight_offset, weight_offset + B') of their
+//    set, so weight_offset * (plain sum of the buckets, row `plain_level`) is added; out_xyzz != nullptr: the result
+//    stays in XYZZ for k_msm_parts_sum.
 __global__ void __launch_bounds__(FINISH_THREADS) k_msm_finish(const xyzz_t* __restrict__ level_sums, const ReduceRows rows, uint32_t c,
-                                                               jac_t* __restrict__ out)
+                                                               jac_t* __restrict__ out, uint32_t plain_level, uint32_t weight_offset,
+                                                               xyzz_t* __restrict__ out_xyzz)
 {
     extern __shared__ xyzz_t sm_sets[]; // S entries
     const Team tm = team_of_lane();
@@ -922,6 +928,15 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_msm_finish(const xyzz_t* __r
             }
             xyzz_t r = xyzz_load(level_sums + (size_t)level * S + set);
             xyzz_add_team(tm, v, r);
+        }
+        if (weight_offset != 0) {
+            const xyzz_t plain = xyzz_load(level_sums + (size_t)plain_level * S + set);
+            xyzz_t m = plain;
+            for (int bit = 30 - __clz(weight_offset); bit >= 0; --bit) {
+                xyzz_dbl_team(tm, m);
+                if ((weight_offset >> bit) & 1) xyzz_add_team(tm, m, plain);
+            }
+            xyzz_add_team(tm, v, m);
         }
         if (tm.r == 0) sm_sets[set] = v;
     }
@@ -938,6 +953,30 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_msm_finish(const xyzz_t* __r
         }
         xyzz_t s = sm_sets[r];
         xyzz_add_team(tm, acc, s);
+    }
+    if (tm.r == 0) {
+        if (out_xyzz != nullptr) {
+            xyzz_store(out_xyzz, acc);
+            return;
+        }
+        jac_t j = xyzz_to_jacobian(acc);
+        fe_store(&out->x, j.x);
+        fe_store(&out->y, j.y);
+        fe_store(&out->z, j.z);
+    }
+}
+
+// sum of the per-part results of one MSM (msm_device: parts), XYZZ -> Jacobian; one team
+__global__ void __launch_bounds__(32) k_msm_parts_sum(const xyzz_t* __restrict__ parts, uint32_t count, jac_t* __restrict__ out)
+{
+    const Team tm = team_of_lane();
+    if (threadIdx.x >= 4) {
+        return;
+    }
+    xyzz_t acc = xyzz_load(parts);
+    for (uint32_t i = 1; i < count; ++i) {
+        const xyzz_t x = xyzz_load(parts + i);
+        xyzz_add_team(tm, acc, x);
     }
     if (tm.r == 0) {
         jac_t j = xyzz_to_jacobian(acc);
@@ -1177,7 +1216,7 @@ int msm_precompute_device(Context* ctx, void* d_table, size_t n, const MsmLevels
 // Device-pointer MSM over table entries [base, base + n) of level 0 (and the same range of every other level).
 //   lv.L == 1: plain points (any stride), W bucket sets.   lv.L > 1: fixed-base levels, S = D / c bucket sets.
 int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, const void* d_points, size_t point_stride,
-               const MsmLevels& lv_in, size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival)
+               const MsmLevels& lv_in, size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival, bool allow_parts)
 {
     Profiler& pr = ctx->prof;
     pr.begin();
@@ -1206,7 +1245,8 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
         return BBG_ERR_ARG;
     }
     int rc;
-    if ((rc = ws.counts.reserve((G + 1) * 4 + 64))) return rc;
+    constexpr int MAX_PARTS = Context::MSM_MAX_PARTS;
+    if ((rc = ws.counts.reserve((G + 1) * 4 + 64 * MAX_PARTS))) return rc;
     if ((rc = ws.offsets.reserve((G + 1) * 4))) return rc;
     if ((rc = ws.cursors.reserve((G + 1) * 4))) return rc;
     if ((rc = ws.sorted.reserve(max_entries * 4))) return rc;
@@ -1216,10 +1256,10 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
     uint32_t* cursors = (uint32_t*)ws.cursors.p;
     uint32_t* sorted = (uint32_t*)ws.sorted.p;
     xyzz_t* buckets = (xyzz_t*)ws.buckets.p;
-    uint32_t* pending = counts + G + 1; // 15 merge-level counters behind the histogram (zeroed with it)
+    uint32_t* pending = counts + G + 1; // 15 merge-level counters (per part) behind the histogram (zeroed with it)
 
     pr.mark(st, PH_MSM_DIGITS);
-    BBG_CUDA(cudaMemsetAsync(counts, 0, (G + 1) * 4 + 64, st));
+    BBG_CUDA(cudaMemsetAsync(counts, 0, (G + 1) * 4 + 64 * MAX_PARTS, st));
     BBG_CUDA(cudaMemsetAsync(buckets, 0, G * sizeof(xyzz_t), st)); // all-zero XYZZ = infinity
 
     DigitParams dp;
@@ -1345,110 +1385,160 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
             n_in = 2 * workers;
         }
     }
-    if ((rc = ws.partials.reserve(slots_total * sizeof(Slot)))) return rc;
-    Slot* slots = (Slot*)ws.partials.p;
-
-    pr.mark(st, PH_MSM_ACCUMULATE);
-    if (J > 0) {
-        k_msm_accumulate<true><<<div_up(num_chunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
-            nullptr, acc_offsets, (uint32_t)G, (uint32_t)chunk, (uint32_t)num_chunks, acc_points, 1, buckets, slots, pending);
-    } else {
-        k_msm_accumulate<false><<<div_up(num_chunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
-            sorted, offsets, (uint32_t)G, (uint32_t)chunk, (uint32_t)num_chunks, (const affine_t*)d_points, (uint32_t)point_stride,
-            buckets, slots, pending);
+    // ---- parts: a single large MSM over one bucket set is cut into H contiguous bucket ranges.  Each range runs its own
+    // accumulate -> slot merge -> bucket reduction chain; the chains of ranges H-1 .. 1 go to high-priority side streams and
+    // the chain of range 0 follows on `st`, so the GPU sees one continuous supply of accumulation CTAs while the latency-bound
+    // tail of every range but the last runs underneath.  Range h's reduction adds (h B / H) * (plain sum of its buckets)
+    // for the weights it does not see.  The results are summed by k_msm_parts_sum.
+    unsigned H = 1;
+    if (allow_parts && J == 0 && S == 1) {
+        const unsigned want = env_uint("BBG_MSM_PARTS", B >= (1u << 18) ? 2u : 1u);
+        while (H * 2 <= want && H * 2 <= (unsigned)MAX_PARTS && (B / (H * 2)) >= (1u << 12)) H *= 2;
     }
-    ctx->launches += 1;
-    pr.mark(st, PH_MSM_FIXUP);
-    {
-        size_t n_in = 2 * num_chunks;
-        Slot* in = slots;
-        unsigned level = 0;
-        while (true) {
-            const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
-            Slot* out = in + n_in;
-            if (level < MERGE_GRID_LEVELS) {
-                k_msm_merge<<<div_up(workers * 4, 128), 128, 0, st>>>(in, (uint32_t)n_in, (uint32_t)workers, pending + level, buckets, out,
-                                                                     pending + level + 1);
-                ctx->launches += 1;
-            } else {
-                k_msm_merge_rest<<<1, MERGE_REST_THREADS, 0, st>>>(in, (uint32_t)n_in, level, pending, buckets);
-                ctx->launches += 1;
-                break;
-            }
-            ++level;
-            if (workers == 1) break;
-            in = out;
-            n_in = 2 * workers;
-        }
-    }
+    const uint32_t Bp = B / H; // buckets per part (H = 1: all of them; S sets are only cut when S = 1)
+    if ((rc = ws.partials.reserve(H * slots_total * sizeof(Slot)))) return rc;
 
-    // bucket reduction (see the comment above k_msm_segments)
-    pr.mark(st, PH_MSM_REDUCE);
-    {
-        // Level 0 sweeps all B buckets (2 additions each, throughput bound once B is large): short segments there give
-        // many workers; level 1 sweeps the B / ell0 segment sums with cooperative teams.
+    // bucket reduction of `sets` sets of `nb` buckets: geometry and scratch size
+    struct ReducePlan {
+        ReduceRows rows;
+        uint32_t segs0, count1, segs1, parts;
+        unsigned sh0, sh1;
+        bool team0;
+        size_t total_segs, n_rows, elems;
+    };
+    auto plan_reduce = [&](uint32_t nb, bool plain) {
+        // Level 0 sweeps all buckets (2 additions each, throughput bound once there are many): short segments there give
+        // many workers; level 1 sweeps the nb / ell0 segment sums with cooperative teams.
         // Measured on B200, 2^19 buckets (ms of bucket reduction; round 1's shape ell0 = 16, ell1 = 4 with plain additions: 0.65):
         // teams at both levels 16/4: 0.65, 4/16: 0.77; plain level 0 + team level 1: 4/8 0.61, 4/16 0.53, 4/32 0.58,
         // 8/8 0.51, 8/16 0.53, 2/16 0.73.  Small bucket sets (2^15 buckets, c = 16): teams at both levels, 4/4: 0.18 (0.34).
-        const bool big = B >= (1u << 18);
-        const unsigned sh0 = std::min(6u, env_uint("BBG_MSM_ELL0_LOG2", big ? 3u : 2u));
-        const unsigned sh1 = std::min(6u, env_uint("BBG_MSM_ELL1_LOG2", big ? 3u : 2u));
-        const bool team0 = env_uint("BBG_MSM_SEG0_TEAM", ((size_t)S * (B >> sh0)) < (1u << 16) ? 1u : 0u) != 0;
-        ReduceRows rows;
-        memset(&rows, 0, sizeof(rows));
-        rows.S = (uint32_t)S;
-        const uint32_t segs0 = (B + (1u << sh0) - 1) >> sh0;
-        const uint32_t count1 = segs0 - 1; // level 1 works on T[1..]
-        const uint32_t segs1 = (count1 + (1u << sh1) - 1) >> sh1;
-        rows.levels = count1 ? 2 : 1;
-        rows.shift[0] = sh0;
-        rows.m[0] = segs0;
-        rows.off[0] = 0;
-        rows.shift[1] = sh1;
-        rows.m[1] = segs1;
-        rows.off[1] = (uint32_t)((size_t)segs0 * S);
-        const size_t total_segs = (size_t)segs0 + segs1;
-        const unsigned levels = rows.levels;
-        // parts: every first-stage CTA sums <= 2 entries per thread, the second stage <= 2 per thread as well
-        // first stage: <= ~4 entries per team; second stage: parts / 64 per team
-        const uint32_t parts = std::min<uint32_t>(2 * TREE_TEAMS, std::max<uint32_t>(1, segs0 / (4 * TREE_TEAMS)));
-        const size_t n_rows = (size_t)levels * S;
+        ReducePlan rp;
+        const bool big = nb >= (1u << 17);
+        rp.sh0 = std::min(6u, env_uint("BBG_MSM_ELL0_LOG2", big ? 3u : 2u));
+        rp.sh1 = std::min(6u, env_uint("BBG_MSM_ELL1_LOG2", big ? 3u : 2u));
+        rp.team0 = env_uint("BBG_MSM_SEG0_TEAM", ((size_t)S * (nb >> rp.sh0)) < (1u << 16) ? 1u : 0u) != 0;
+        memset(&rp.rows, 0, sizeof(rp.rows));
+        rp.rows.S = (uint32_t)S;
+        rp.segs0 = (nb + (1u << rp.sh0) - 1) >> rp.sh0;
+        rp.count1 = rp.segs0 - 1; // level 1 works on T[1..]
+        rp.segs1 = (rp.count1 + (1u << rp.sh1) - 1) >> rp.sh1;
+        rp.rows.levels = rp.count1 ? 2 : 1;
+        rp.rows.shift[0] = rp.sh0;
+        rp.rows.m[0] = rp.segs0;
+        rp.rows.off[0] = 0;
+        rp.rows.shift[1] = rp.sh1;
+        rp.rows.m[1] = rp.segs1;
+        rp.rows.off[1] = (uint32_t)((size_t)rp.segs0 * S);
+        rp.total_segs = (size_t)rp.segs0 + rp.segs1;
+        // the plain sum of all buckets = the sum of the level-0 segment sums T0: one more row for the tree sum
+        rp.rows.m[rp.rows.levels] = rp.segs0;
+        rp.rows.off[rp.rows.levels] = (uint32_t)(rp.total_segs * S);
+        // parts: every first-stage CTA sums <= ~4 entries per team; second stage: parts / 64 per team
+        rp.parts = std::min<uint32_t>(2 * TREE_TEAMS, std::max<uint32_t>(1, rp.segs0 / (4 * TREE_TEAMS)));
+        rp.n_rows = (size_t)(rp.rows.levels + (plain ? 1 : 0)) * S;
         // layout: R0 | V1 | T0 | per-part sums | per-row sums
-        if ((rc = ws.reduce.reserve(((total_segs + segs0) * S + n_rows * parts + n_rows) * sizeof(xyzz_t)))) return rc;
-        xyzz_t* r_all = (xyzz_t*)ws.reduce.p;
-        xyzz_t* t0 = r_all + total_segs * S;
-        xyzz_t* part_out = t0 + (size_t)segs0 * S;
-        xyzz_t* row_out = part_out + n_rows * parts;
+        rp.elems = (rp.total_segs + rp.segs0) * S + rp.n_rows * rp.parts + rp.n_rows;
+        return rp;
+    };
+    const ReducePlan rp = plan_reduce(Bp, H > 1);
+    if ((rc = ws.reduce.reserve((rp.elems * H + MAX_PARTS) * sizeof(xyzz_t)))) return rc;
+    xyzz_t* part_results = (xyzz_t*)ws.reduce.p + rp.elems * H;
+
+    // one part's chain on stream s; the last step writes XYZZ to out_xyzz (parts) or Jacobian to d_out (H = 1)
+    auto run_chain = [&](cudaStream_t s, unsigned h, bool mark) -> int {
+        Slot* slots = (Slot*)ws.partials.p + (size_t)h * slots_total;
+        uint32_t* pend = pending + 16 * h;
+        xyzz_t* bk = buckets + (size_t)h * Bp;
+        const uint32_t g_lo = H > 1 ? h * Bp : 0, g_hi = H > 1 ? (h + 1) * Bp : (uint32_t)G;
+        if (mark) pr.mark(s, PH_MSM_ACCUMULATE);
+        if (J > 0) {
+            k_msm_accumulate<true><<<div_up(num_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>(
+                nullptr, acc_offsets, (uint32_t)G, g_lo, g_hi, (uint32_t)chunk, (uint32_t)num_chunks, acc_points, 1, buckets, slots, pend);
+        } else {
+            k_msm_accumulate<false><<<div_up(num_chunks, ACC_THREADS), ACC_THREADS, 0, s>>>(
+                sorted, offsets, (uint32_t)G, g_lo, g_hi, (uint32_t)chunk, (uint32_t)num_chunks, (const affine_t*)d_points,
+                (uint32_t)point_stride, buckets, slots, pend);
+        }
+        ctx->launches += 1;
+        if (mark) pr.mark(s, PH_MSM_FIXUP);
         {
-            const uint32_t workers = segs0 * (uint32_t)S;
-            if (team0) {
-                k_msm_segments<false, true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, st>>>(buckets, B, B, 1u << sh0, segs0, workers, r_all, t0);
+            size_t n_in = 2 * num_chunks;
+            Slot* in = slots;
+            unsigned level = 0;
+            while (true) {
+                const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
+                Slot* out = in + n_in;
+                if (level < MERGE_GRID_LEVELS) {
+                    k_msm_merge<<<div_up(workers * 4, 128), 128, 0, s>>>(in, (uint32_t)n_in, (uint32_t)workers, pend + level, buckets, out,
+                                                                        pend + level + 1);
+                    ctx->launches += 1;
+                } else {
+                    k_msm_merge_rest<<<1, MERGE_REST_THREADS, 0, s>>>(in, (uint32_t)n_in, level, pend, buckets);
+                    ctx->launches += 1;
+                    break;
+                }
+                ++level;
+                if (workers == 1) break;
+                in = out;
+                n_in = 2 * workers;
+            }
+        }
+        // bucket reduction (see the comment above k_msm_segments)
+        if (mark) pr.mark(s, PH_MSM_REDUCE);
+        xyzz_t* r_all = (xyzz_t*)ws.reduce.p + rp.elems * h;
+        xyzz_t* t0 = r_all + rp.total_segs * S;
+        xyzz_t* part_out = t0 + (size_t)rp.segs0 * S;
+        xyzz_t* row_out = part_out + rp.n_rows * rp.parts;
+        {
+            const uint32_t workers = rp.segs0 * (uint32_t)S;
+            if (rp.team0) {
+                k_msm_segments<false, true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, s>>>(bk, Bp, Bp, 1u << rp.sh0, rp.segs0, workers, r_all, t0);
             } else {
-                k_msm_segments<false, false><<<div_up(workers, SEG_THREADS), SEG_THREADS, 0, st>>>(buckets, B, B, 1u << sh0, segs0, workers, r_all, t0);
+                k_msm_segments<false, false><<<div_up(workers, SEG_THREADS), SEG_THREADS, 0, s>>>(bk, Bp, Bp, 1u << rp.sh0, rp.segs0, workers, r_all, t0);
             }
             ctx->launches += 1;
         }
-        if (count1) {
-            const uint32_t workers = segs1 * (uint32_t)S;
-            k_msm_segments<true, true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, st>>>(t0 + 1, segs0, count1, 1u << sh1, segs1, workers,
-                                                                                                        r_all + rows.off[1], nullptr);
+        if (rp.count1) {
+            const uint32_t workers = rp.segs1 * (uint32_t)S;
+            k_msm_segments<true, true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, s>>>(t0 + 1, rp.segs0, rp.count1, 1u << rp.sh1, rp.segs1,
+                                                                                                       workers, r_all + rp.rows.off[1], nullptr);
             ctx->launches += 1;
         }
-        k_msm_tree_sum<<<dim3(parts, (unsigned)n_rows), TREE_THREADS, 0, st>>>(r_all, rows, part_out);
+        ReduceRows tree_rows = rp.rows;
+        tree_rows.levels = (uint32_t)(rp.n_rows / S); // + the plain-sum row when the set is cut into parts
+        k_msm_tree_sum<<<dim3(rp.parts, (unsigned)rp.n_rows), TREE_THREADS, 0, s>>>(r_all, tree_rows, part_out);
         ctx->launches += 1;
         const xyzz_t* sums = part_out;
-        if (parts > 1) {
+        if (rp.parts > 1) {
             ReduceRows second;
             memset(&second, 0, sizeof(second));
-            second.S = (uint32_t)n_rows; // every row of the first stage is one "set" of a single level with `parts` entries
+            second.S = (uint32_t)rp.n_rows; // every row of the first stage is one "set" of a single level with `parts` entries
             second.levels = 1;
-            second.m[0] = parts;
-            k_msm_tree_sum<<<dim3(1, (unsigned)n_rows), TREE_THREADS, 0, st>>>(part_out, second, row_out);
+            second.m[0] = rp.parts;
+            k_msm_tree_sum<<<dim3(1, (unsigned)rp.n_rows), TREE_THREADS, 0, s>>>(part_out, second, row_out);
             ctx->launches += 1;
             sums = row_out;
         }
-        pr.mark(st, PH_MSM_COMBINE);
-        k_msm_finish<<<1, FINISH_THREADS, S * sizeof(xyzz_t), st>>>(sums, rows, c, (jac_t*)d_out);
+        if (mark) pr.mark(s, PH_MSM_COMBINE);
+        k_msm_finish<<<1, FINISH_THREADS, S * sizeof(xyzz_t), s>>>(sums, rp.rows, c, (jac_t*)d_out, rp.rows.levels, h * Bp,
+                                                                   H > 1 ? part_results + h : nullptr);
+        ctx->launches += 1;
+        return BBG_OK;
+    };
+
+    if (H == 1) {
+        if ((rc = run_chain(st, 0, true))) return rc;
+    } else {
+        BBG_CUDA(cudaEventRecord(ctx->ev_part_fork, st));
+        for (unsigned h = H - 1; h >= 1; --h) {
+            cudaStream_t s = ctx->part_stream[h - 1];
+            BBG_CUDA(cudaStreamWaitEvent(s, ctx->ev_part_fork, 0));
+            if ((rc = run_chain(s, h, false))) return rc;
+            BBG_CUDA(cudaEventRecord(ctx->ev_part_join[h - 1], s));
+        }
+        if ((rc = run_chain(st, 0, true))) return rc;
+        for (unsigned h = 1; h < H; ++h) BBG_CUDA(cudaStreamWaitEvent(st, ctx->ev_part_join[h - 1], 0));
+        k_msm_parts_sum<<<1, 32, 0, st>>>(part_results, H, (jac_t*)d_out);
         ctx->launches += 1;
     }
     pr.mark(st, -1);

@@ -129,12 +129,27 @@ def ntt_sharded_natural(bbg, block_in, n, kind, rank, world, generator_size=0, c
     return block_out
 
 
-def simulate(bbg, x, kind, world, generator_size=0, constant=None):
-    """All `world` ranks on one device. x: torch CUDA int64 (n, 4) natural order -> natural-order result."""
+def simulate(bbg, x, kind, world, generator_size=0, constant=None, fused=False):
+    """All `world` ranks on one device. x: torch CUDA int64 (n, 4) natural order -> natural-order result.
+    fused: the exchange is done by the pass before it storing into the "peers'" receive buffers (here: buffers of the
+    same device) -- the kernel and index maths of bbg_ntt_dist_fused_dev."""
     import torch
     n = x.shape[0]
     in_pos, out_pos = bbg.ntt_dist_layout(n, world)
     m = n // world
+    if fused:
+        recvs = [torch.zeros((m, 4), dtype=x.dtype, device=x.device) for _ in range(world)]
+        ptrs = [t.data_ptr() for t in recvs]
+        for r in range(world):
+            src = extract_shard(x, in_pos, world, r).contiguous()
+            bbg.ntt_dist_fused_phase0(src, torch.empty_like(src), ptrs, n, kind, r, world, generator_size, constant)
+        out = torch.empty_like(x)
+        for r in range(world):
+            dst = torch.empty_like(recvs[r])
+            bbg.ntt_dist_phase(recvs[r], dst, n, kind, r, world, 1, generator_size, constant)
+            insert_shard(out, dst, out_pos, world, r)
+        torch.cuda.synchronize()
+        return out
     mids = []
     for r in range(world):
         src = extract_shard(x, in_pos, world, r).contiguous()

@@ -14,10 +14,21 @@ def main():
         nmax = min(nmax, 4096)
     if logs:
         t0 = time.time(); pip = bbg.Pippenger.from_path(srs_dir, nmax); print('srs load+decode %.3fs' % (time.time() - t0))
-    bbg.profile(True)
+    plain = os.environ.get('DEVBENCH_PLAIN', '0') == '1'  # no per-phase events: mean of 10 calls, L2 flushed in between
+    bbg.profile(not plain)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     for lg in logs:
         n = min(1 << lg, nmax)
         sc = torch.from_numpy(inputs.fr_elements(7, n).view(np.int64)).cuda()
+        if plain:
+            tot = 0.0
+            for it in range(13):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                flush.zero_()
+                e0.record(); out = pip.pippenger_unsafe(sc, 0, n); e1.record(); torch.cuda.synchronize()
+                if it >= 3: tot += e0.elapsed_time(e1)
+            print('MSM 2^%d: %.3f ms (mean of 10, no phase events)' % (lg, tot / 10))
+            continue
         for it in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); out = pip.pippenger_unsafe(sc, 0, n); e1.record(); torch.cuda.synchronize()

@@ -368,6 +368,31 @@ def test_msm_fixed_base_levels(bbg, orc, srs_mini, levels, c, monkeypatch):
     assert orc.jac_to_buffer(pip.pippenger_unsafe(one, 0, n)) == orc.jac_to_buffer(orc.pippenger(one, pts[:n], stride=1))
 
 
+@pytest.mark.parametrize("parts,c", [(2, 14), (4, 15), (2, 16), (4, 14), (1, 14)])
+def test_msm_bucket_range_parts(bbg, orc, srs_mini, parts, c, monkeypatch):
+    """msm.cu "parts": one bucket set cut into contiguous bucket ranges, each with its own accumulate -> merge -> reduce
+    chain on its own stream (range h adds h B / H times the plain sum of its buckets), summed at the end.  Same group
+    element as the oracle for uniform, skewed (every digit in one bucket) and sub-range inputs; (4, 14) asks for more
+    parts than the bucket count allows and must fall back to fewer."""
+    pts, table = srs_mini
+    monkeypatch.setenv("BBG_MSM_PARTS", str(parts))
+    monkeypatch.setenv("BBG_MSM_C", str(c))
+    pip = bbg.Pippenger.from_points(pts)
+    n = 4000
+    sc = inputs.fr_elements(1970 + parts + c, n, coarse_fraction=0.2)
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(sc, 0, n)) == orc.jac_to_buffer(orc.pippenger(sc, pts[:n], stride=1))
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(sc[:333], 55, 333)) == orc.jac_to_buffer(orc.pippenger(sc[:333], pts[55:388], stride=1))
+    one = np.repeat(inputs.fr_elements(6, 1), n, axis=0)
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(one, 0, n)) == orc.jac_to_buffer(orc.pippenger(one, pts[:n], stride=1))
+    # digits only in the top bucket range / only in the bottom one: small scalars (low windows, low buckets) and r - small
+    small_m = orc.to_mont(po.FR, list(range(1, 501)))
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(small_m, 0, 500)) == orc.jac_to_buffer(orc.pippenger(small_m, pts[:500], stride=1))
+    neg_m = orc.to_mont(po.FR, [po.FR_MODULUS - k for k in range(1, 501)]) if hasattr(po, "FR_MODULUS") else orc.field_op(po.FR, po.OP_NEG, small_m)
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(neg_m, 0, 500)) == orc.jac_to_buffer(orc.pippenger(neg_m, pts[:500], stride=1))
+    back = pip.pippenger_unsafe(sc, 0, n)  # the same call again: workspaces and counters are reusable
+    assert orc.jac_to_buffer(back) == orc.jac_to_buffer(orc.pippenger(sc, pts[:n], stride=1))
+
+
 @pytest.mark.parametrize("lg,world", [(12, 2), (14, 4), (16, 8), (18, 8), (20, 2)])
 def test_ntt_multi_gpu_data_path_simulated(bbg, orc, lg, world):
     """The multi-GPU four-step NTT (phase 0 / all-to-all / phase 1, csrc/ntt.cu + bbg/dist_ntt.py) with every rank run in
@@ -384,6 +409,23 @@ def test_ntt_multi_gpu_data_path_simulated(bbg, orc, lg, world):
         assert np.array_equal(canon(orc, got), canon(orc, exp)), (lg, world, kind)
     if lg <= 14:
         assert np.array_equal(canon(orc, exp), canon(orc, orc.ntt(po.NTT_IFFT_CONST, x, constant=const)))
+
+
+@pytest.mark.parametrize("lg,world", [(12, 2), (14, 4), (16, 8), (18, 8), (20, 2), (22, 4)])
+def test_ntt_fused_exchange_simulated(bbg, orc, lg, world):
+    """bbg_ntt_dist_fused_dev: the pass before the exchange stores every element straight into the owner's receive
+    buffer (NVLink peer memory in the torchrun path, buffers of the same device here) at the slot the all-to-all would
+    have used; phase 1 on those buffers must reproduce the single-array transform bit for bit."""
+    import torch
+    from bbg import dist_ntt
+    n = 1 << lg
+    x = inputs.fr_elements(3300 + lg, n, coarse_fraction=0.25)
+    const = inputs.fr_elements(3400 + lg, 1)[0]
+    xt = torch.from_numpy(x.view(np.int64)).cuda()
+    for kind, gs in ((bbg.FFT, 0), (bbg.COSET_FFT, n // 4), (bbg.COSET_IFFT, 0), (bbg.IFFT_WITH_CONSTANT, 0)):
+        got = dist_ntt.simulate(bbg, xt, kind, world, generator_size=gs, constant=const, fused=True).cpu().numpy().view(np.uint64)
+        exp = bbg.ntt(x.copy(), kind, generator_size=gs, constant=const)
+        assert np.array_equal(canon(orc, got), canon(orc, exp)), (lg, world, kind)
 
 
 def test_multi_process_nccl_paths(bbg):
