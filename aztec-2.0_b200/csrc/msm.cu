@@ -1385,14 +1385,19 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
             n_in = 2 * workers;
         }
     }
-    // ---- parts: a single large MSM over one bucket set is cut into H contiguous bucket ranges.  Each range runs its own
-    // accumulate -> slot merge -> bucket reduction chain; the chains of ranges H-1 .. 1 go to high-priority side streams and
-    // the chain of range 0 follows on `st`, so the GPU sees one continuous supply of accumulation CTAs while the latency-bound
-    // tail of every range but the last runs underneath.  Range h's reduction adds (h B / H) * (plain sum of its buckets)
-    // for the weights it does not see.  The results are summed by k_msm_parts_sum.
+    // ---- parts (experiment, OFF by default: BBG_MSM_PARTS = 2 | 4): a single large MSM over one bucket set is cut into H
+    // contiguous bucket ranges.  Each range runs its own accumulate -> slot merge -> bucket reduction chain; the chains of
+    // ranges H-1 .. 1 go to high-priority side streams and the chain of range 0 follows on `st`, the idea being that the
+    // latency-bound tail of every range but the last runs underneath the accumulation of the next.  Range h's reduction adds
+    // (h B / H) * (plain sum of its buckets) for the weights it does not see; k_msm_parts_sum adds the results.
+    // Measured on B200 (2^20 points, c = 20): 3.41 ms with 2 parts, 3.65 with 4, against 3.12 ms uncut (2^18: 1.64 / 1.76 /
+    // 1.35).  The accumulation's CTAs fill the register file (4 x 128 threads x 128 registers per SM) and each lives for
+    // about a third of the kernel, so the tail kernels of the side streams -- priority or not -- only find SM slots at the
+    // wave boundaries and end up running beside the LAST range's tail instead of under its accumulation, while the extra
+    // launches and the offset doublings are paid in full.  Kept (parity-tested) for parts with a finer-grained block scheduler.
     unsigned H = 1;
     if (allow_parts && J == 0 && S == 1) {
-        const unsigned want = env_uint("BBG_MSM_PARTS", B >= (1u << 18) ? 2u : 1u);
+        const unsigned want = env_uint("BBG_MSM_PARTS", 1u);
         while (H * 2 <= want && H * 2 <= (unsigned)MAX_PARTS && (B / (H * 2)) >= (1u << 12)) H *= 2;
     }
     const uint32_t Bp = B / H; // buckets per part (H = 1: all of them; S sets are only cut when S = 1)
