@@ -268,13 +268,34 @@ template <> __device__ __forceinline__ void radix_round<3, false>(fr (&x)[8], ui
 // TMA_TW: one thread issues a TMA bulk copy (cp.async.bulk, completion on an mbarrier) of this pass's stage-twiddle table
 // (2^(g-1) entries, <= 4 KB) into shared memory behind the exchange buffer; the copy flies while the threads load their
 // elements from HBM, and the radix rounds then read twiddles from shared memory instead of the L1 / read-only path.
+// PERSIST (experiment, OFF by default: BBG_NTT_PERSIST=1): the grid is one wave of resident CTAs and every CTA walks over its
+// tile groups; the elements of the NEXT group are fetched with cp.async (LDGSTS, 16 bytes per request, no registers) into a
+// staging area behind the exchange buffer while the current group is in its radix rounds, the idea being that a CTA never
+// sits in a load phase with nothing to multiply.  Measured on B200 (fft, ms, one-group-per-CTA -> persistent): 2^20 0.254 ->
+// 0.298, 2^22 0.906 -> 1.017, 2^24 3.55 -> 4.06, 2^26 16.2 -> 18.7: 12-15 % SLOWER.  The hardware's own CTA turnover already
+// overlaps one CTA's loads with its neighbours' arithmetic, and the persistent form pays two more block barriers per group,
+// 12-32 more spilled bytes and an extra trip through shared memory.  Kept, parity-tested, as the record of the experiment.
+//   !LAST: a thread stages exactly the elements it will own (slot = (j, half) * threads + thread: conflict-free, no barrier);
+//   LAST : rows are contiguous in memory, lanes run along the rows and the staging area has the exchange layout (the
+//          transposition the non-persistent form does through registers).
 static constexpr int NTT_TW_SMEM_BYTES = 128 * 32;
-template <int LOGE, bool LAST, int CTAS = NttGeom<LOGE>::MIN_CTAS, bool TMA_TW = false>
+static constexpr int NTT_PERSIST_SMEM_BYTES = 2 * NttGeom<2>::SMEM_BYTES + NTT_TW_SMEM_BYTES; // exchange + staging + twiddles = 69,632 B
+static constexpr bool NTT_PERSIST_DEFAULT = false; // BBG_NTT_PERSIST overrides
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int LOGE, bool LAST, int CTAS = NttGeom<LOGE>::MIN_CTAS, bool TMA_TW = false, bool PERSIST = false>
 __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams P)
 {
     extern __shared__ uint4 sm[];
     constexpr int E = NttGeom<LOGE>::E;
     const uint32_t half_stride = NttGeom<LOGE>::HALF_STRIDE;
+    uint4* const stage = sm + 2 * NttGeom<LOGE>::HALF_STRIDE + (TMA_TW ? NTT_TW_SMEM_BYTES / 16 : 0); // PERSIST only
     using tw_barrier = cuda::barrier<cuda::thread_scope_block>;
 #pragma nv_diag_suppress static_var_with_dynamic_init
     __shared__ tw_barrier tw_bar;
@@ -306,62 +327,135 @@ __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams
     const uint32_t q = tau >> LOGE;               // [0, R/E)
     const uint32_t Nmask = (1u << P.tw_log_n) - 1u;         // full transform (twiddle exponents); n <= 2^28: 32-bit index maths throughout
     const uint32_t num_tiles = (1u << P.log_n) >> (g + LOGE); // local array
-    const uint32_t tile = blockIdx.x * tiles_per_cta + tile_local;
-    const bool active = tile < num_tiles;
     const uint32_t rows8 = R >> LOGE;
+    const uint32_t num_groups = (num_tiles + tiles_per_cta - 1) / tiles_per_cta;
 
-    // ---- tile coordinates
-    uint32_t in_base = 0;     // element index of (row 0, col 0)
-    uint32_t rest0 = 0;       // non-last: first value of the low index; last: first o_1 of the tile
-    uint32_t mid = 0;
-    if constexpr (!LAST) {
-        const uint32_t chunk_bits = P.below - LOGE; // log2(column chunks per hi value)
-        const uint32_t hi = tile >> chunk_bits;
-        rest0 = (tile & ((1u << chunk_bits) - 1u)) << LOGE;
-        in_base = (hi << (g + P.below)) + rest0;
-    } else {
-        const uint32_t o1_bits = P.g1 - LOGE;
-        rest0 = (tile & ((1u << o1_bits) - 1u)) << LOGE;
-        mid = tile >> o1_bits;
+    // source element index of item (it, thread) of the last pass's row-contiguous load
+    auto last_src_index = [&](uint32_t rest0, uint32_t mid, uint32_t c, uint32_t row) -> uint32_t {
+        const uint32_t hi_idx = ((rest0 + c) << P.mid_bits_total) | mid;
+        if (P.rk_bits == 0) {
+            return (hi_idx << g) + row;
+        }
+        // after the all-to-all the row is split by source rank: chunk s holds i_P = (s, low)
+        const uint32_t src_rank = row >> P.split_low, low = row & ((1u << P.split_low) - 1);
+        return (src_rank << P.chunk_log) + (hi_idx << P.split_low) + low;
+    };
+    auto tile_coords = [&](uint32_t tile, uint32_t& in_base, uint32_t& rest0, uint32_t& mid) {
+        in_base = 0; // element index of (row 0, col 0)
+        mid = 0;
+        if constexpr (!LAST) {
+            const uint32_t chunk_bits = P.below - LOGE; // log2(column chunks per hi value)
+            const uint32_t hi = tile >> chunk_bits;
+            rest0 = (tile & ((1u << chunk_bits) - 1u)) << LOGE; // first value of the low index
+            in_base = (hi << (g + P.below)) + rest0;
+        } else {
+            const uint32_t o1_bits = P.g1 - LOGE;
+            rest0 = (tile & ((1u << o1_bits) - 1u)) << LOGE; // first o_1 of the tile
+            mid = tile >> o1_bits;
+        }
+    };
+    // PERSIST: start the copies of tile group `grp` into the staging area
+    auto prefetch = [&](uint32_t grp) {
+        const uint32_t t = grp * tiles_per_cta + tile_local;
+        if (t < num_tiles) {
+            uint32_t ib, r0, md;
+            tile_coords(t, ib, r0, md);
+            if constexpr (!LAST) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    const uint32_t row = (uint32_t)j * rows8 + q;
+                    const uint4* src = reinterpret_cast<const uint4*>(P.src + (ib + (row << P.below) + col));
+                    cp_async16(stage + (2 * j) * NTT_THREADS + threadIdx.x, src);
+                    cp_async16(stage + (2 * j + 1) * NTT_THREADS + threadIdx.x, src + 1);
+                }
+            } else {
+#pragma unroll
+                for (uint32_t it = 0; it < (uint32_t)E; ++it) {
+                    const uint32_t idx = it * R + tau; // [0, E R): column-major
+                    const uint32_t c = idx >> g, row = idx & (R - 1);
+                    const uint4* src = reinterpret_cast<const uint4*>(P.src + last_src_index(r0, md, c, row));
+                    const uint32_t si = sm_idx<LOGE>(tile_local, R, row, c);
+                    cp_async16(stage + si, src);
+                    cp_async16(stage + half_stride + si, src + 1);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    uint32_t group = blockIdx.x;
+    bool tw_pending = TMA_TW;
+    if constexpr (PERSIST) {
+        prefetch(group);
     }
+    while (true) {
+    const uint32_t tile = group * tiles_per_cta + tile_local;
+    const bool active = tile < num_tiles;
+    uint32_t in_base, rest0, mid;
+    tile_coords(tile, in_base, rest0, mid);
 
     fr x[E];
+    // the coset pre-scale of the first pass, fused into the load
+    auto pre_scale = [&](fr& v, uint32_t a) {
+        const uint32_t at = (uint32_t)insert_bits(a, P.rk_pos, P.rk_bits, P.rk_val); // true coefficient index
+        if (P.pro_full != nullptr) {
+            if (at < P.pro_size) v = fe_mul(v, fe_load_nc<FrParams>(P.pro_full + at));
+        } else if (P.pro_lo != nullptr && at < P.pro_size) {
+            fr sc = fe_mul(fe_load_nc<FrParams>(P.pro_hi + (at >> P.pro_split)),
+                           fe_load_nc<FrParams>(P.pro_lo + (at & ((1u << P.pro_split) - 1u))));
+            v = fe_mul(v, sc);
+        }
+    };
     // ---- load (round-0 register layout: rows j * R/8 + q, column col)
-    if constexpr (!LAST) {
+    if constexpr (PERSIST) {
+        cp_async_wait_all();
+        __syncthreads(); // the staged elements are visible to every thread, and the exchange buffer is free again
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                if constexpr (!LAST) {
+                    const uint4 a = stage[(2 * j) * NTT_THREADS + threadIdx.x], b = stage[(2 * j + 1) * NTT_THREADS + threadIdx.x];
+                    x[j].l[0] = a.x; x[j].l[1] = a.y; x[j].l[2] = a.z; x[j].l[3] = a.w;
+                    x[j].l[4] = b.x; x[j].l[5] = b.y; x[j].l[6] = b.z; x[j].l[7] = b.w;
+                } else {
+                    const uint32_t row = (uint32_t)j * rows8 + q;
+                    x[j] = smem_load(stage, half_stride, sm_idx<LOGE>(tile_local, R, row, col));
+                }
+            }
+        }
+        if constexpr (LAST) {
+            __syncthreads(); // every thread has taken its elements: the staging area may be refilled
+        }
+        if (group + gridDim.x < num_groups) {
+            prefetch(group + gridDim.x);
+        }
+        if constexpr (!LAST) {
+            if (active && (P.pro_full != nullptr || P.pro_lo != nullptr)) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    const uint32_t row = (uint32_t)j * rows8 + q;
+                    pre_scale(x[j], in_base + (row << P.below) + col);
+                }
+            }
+        }
+    } else if constexpr (!LAST) {
         if (active) {
 #pragma unroll
             for (int j = 0; j < E; ++j) {
                 const uint32_t row = (uint32_t)j * rows8 + q;
                 const uint32_t a = in_base + (row << P.below) + col;
                 x[j] = fe_load<FrParams>(P.src + a);
-                const uint32_t at = (uint32_t)insert_bits(a, P.rk_pos, P.rk_bits, P.rk_val); // true coefficient index
-                if (P.pro_full != nullptr) {
-                    if (at < P.pro_size) x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.pro_full + at));
-                } else if (P.pro_lo != nullptr && at < P.pro_size) {
-                    fr s = fe_mul(fe_load_nc<FrParams>(P.pro_hi + (at >> P.pro_split)),
-                                  fe_load_nc<FrParams>(P.pro_lo + (at & ((1u << P.pro_split) - 1u))));
-                    x[j] = fe_mul(x[j], s);
-                }
+                pre_scale(x[j], a);
             }
         }
     } else {
         // rows are contiguous in memory: stage through shared memory with lanes along the rows
         if (active) {
-            const uint32_t mid_bits_total = P.mid_bits_total;
 #pragma unroll 1
             for (uint32_t it = 0; it < (uint32_t)E; ++it) {
                 const uint32_t idx = it * R + tau;   // [0, E R): column-major
                 const uint32_t c = idx >> g, row = idx & (R - 1);
-                const uint32_t hi_idx = ((rest0 + c) << mid_bits_total) | mid;
-                uint32_t a;
-                if (P.rk_bits == 0) {
-                    a = (hi_idx << g) + row;
-                } else {
-                    // after the all-to-all the row is split by source rank: chunk s holds i_P = (s, low)
-                    const uint32_t src_rank = row >> P.split_low, low = row & ((1u << P.split_low) - 1);
-                    a = (src_rank << P.chunk_log) + (hi_idx << P.split_low) + low;
-                }
-                fr v = fe_load<FrParams>(P.src + a);
+                fr v = fe_load<FrParams>(P.src + last_src_index(rest0, mid, c, row));
                 smem_store(sm, half_stride, sm_idx<LOGE>(tile_local, R, row, c), v);
             }
         }
@@ -394,7 +488,10 @@ __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams
         }
         const uint32_t lo_part = q & ((1u << w0) - 1);
         if constexpr (TMA_TW) {
-            if (first) tw_bar.wait(std::move(tw_token)); // the twiddles have landed (every thread waits: inactive ones too)
+            if (tw_pending) { // the twiddles have landed (every thread waits: inactive ones too); once per CTA
+                tw_bar.wait(std::move(tw_token));
+                tw_pending = false;
+            }
         }
         if (active) {
             radix_round<LOGE, TMA_TW>(x, g, w0, (uint32_t)b_hi, lo_part, stage_tw);
@@ -417,9 +514,7 @@ __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams
     }
 
     // ---- store.  After the last round (w0 == 0) thread holds rows (q << LOGE) | j; row rho holds X[bitrev_g(rho)].
-    if (!active) {
-        return;
-    }
+    if (active) {
     if constexpr (!LAST) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
@@ -475,6 +570,15 @@ __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams
             fe_store(P.dst + (((size_t)ol << P.out_shift) + P.out_off), x[j]);
         }
     }
+    } // active
+    if constexpr (!PERSIST) {
+        break;
+    }
+    group += gridDim.x;
+    if (group >= num_groups) {
+        break;
+    }
+    } // tile groups
 }
 
 // ---- N <= 32: direct O(N^2) DFT by one warp (everything fused, nothing worth tiling)
@@ -875,6 +979,8 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, true, 3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES + NTT_TW_SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, false, 3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES + NTT_TW_SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, true, 3, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_PERSIST_SMEM_BYTES));
+        BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, false, 3, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_PERSIST_SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute((k_ntt_pass<2, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<2>::SMEM_BYTES));
         BBG_CUDA(cudaFuncSetAttribute(k_ntt_pass<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttGeom<1>::SMEM_BYTES));
@@ -892,6 +998,10 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
     static const bool tma_twiddles = [] {
         const char* v = getenv("BBG_NTT_TMA_TWIDDLES"); // default on; 0 = read the stage twiddles through the read-only path
         return !(v && *v == '0');
+    }();
+    static const int persist_env = [] {
+        const char* v = getenv("BBG_NTT_PERSIST"); // 1: persistent CTAs with cp.async prefetch of the next tile group (E = 4); 0: one tile group per CTA
+        return v && *v ? atoi(v) : -1;
     }();
     static const bool e4_two_ctas = [] {
         const char* v = getenv("BBG_NTT_E4_CTAS");
@@ -1002,6 +1112,10 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
             // experiment knob (BBG_NTT_E4_CTAS=2): 128 registers, no spills, 4 instead of 6 warps per scheduler
             if (last) k_ntt_pass<2, true, 2><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
             else k_ntt_pass<2, false, 2><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES, st>>>(pp);
+        } else if (loge == 2 && tma_twiddles && (persist_env > 0 || (persist_env < 0 && NTT_PERSIST_DEFAULT)) && blocks > 3u * ctx->num_sms) {
+            const unsigned grid = 3u * (unsigned)ctx->num_sms; // one wave: three CTAs per SM
+            if (last) k_ntt_pass<2, true, 3, true, true><<<grid, NTT_THREADS, NTT_PERSIST_SMEM_BYTES, st>>>(pp);
+            else k_ntt_pass<2, false, 3, true, true><<<grid, NTT_THREADS, NTT_PERSIST_SMEM_BYTES, st>>>(pp);
         } else if (loge == 2 && tma_twiddles) {
             if (last) k_ntt_pass<2, true, 3, true><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES + NTT_TW_SMEM_BYTES, st>>>(pp);
             else k_ntt_pass<2, false, 3, true><<<blocks, NTT_THREADS, NttGeom<2>::SMEM_BYTES + NTT_TW_SMEM_BYTES, st>>>(pp);

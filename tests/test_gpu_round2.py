@@ -282,3 +282,33 @@ def test_stats_totals_count_pcie_bytes(bbg):
         assert t3["ntt"]["h2d"] == t2["ntt"]["h2d"] and t3["ntt"]["d2h"] - t2["ntt"]["d2h"] == x.nbytes
     finally:
         bbg.resident_mode(False)
+
+
+def test_ntt_persistent_prefetch_variant_matches_default(bbg):
+    """k_ntt_pass<.., PERSIST> (persistent CTAs, cp.async prefetch of the next tile group; BBG_NTT_PERSIST=1, an
+    experiment that measured slower and is off by default): the knob is read once per process, so the variant runs in a
+    child process and its fft / coset_fft / coset_ifft of a 2^20 array must equal this process's default kernels bit for bit."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    n = 1 << 20
+    x = inputs.fr_elements(4242, n)
+    here = {}
+    for kind in (bbg.FFT, bbg.COSET_FFT, bbg.COSET_IFFT):
+        here[kind] = hashlib.sha256(bbg.ntt(x.copy(), kind).tobytes()).hexdigest()
+    code = (
+        "import sys, hashlib\n"
+        "sys.path[:0] = ['.', 'tests', 'aztec-2.0_b200/python']\n"
+        "import bbg, inputs\n"
+        "bbg.init(0)\n"
+        "x = inputs.fr_elements(4242, 1 << 20)\n"
+        "for kind in (bbg.FFT, bbg.COSET_FFT, bbg.COSET_IFFT):\n"
+        "    print(kind, hashlib.sha256(bbg.ntt(x.copy(), kind).tobytes()).hexdigest())\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BBG_NTT_PERSIST="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = dict((int(l.split()[0]), l.split()[1]) for l in r.stdout.strip().splitlines())
+    assert got == here
