@@ -1084,7 +1084,8 @@ int bbg_ntt(void* coeffs, size_t n, int kind, size_t generator_size, const void*
 int bbg_ntt_ex(void* coeffs, size_t n, int kind, size_t generator_size, const void* constant, unsigned flags)
 {
     GET_CTX();
-    return ntt_host(ctx, coeffs, n, kind, generator_size, constant, (flags & BBG_KEEP_ON_DEVICE) != 0);
+    const bool keep = (flags & BBG_KEEP_ON_DEVICE) != 0 || ((flags & BBG_KEEP_IF_AHEAD) != 0 && resident_is_ahead(ctx, coeffs, n * 32));
+    return ntt_host(ctx, coeffs, n, kind, generator_size, constant, keep);
 }
 
 int bbg_ntt_dist_layout(size_t n, int world, unsigned* in_pos, unsigned* out_pos)

@@ -481,7 +481,7 @@ int bbg_wire_coset_fft(const void* wire, void* wire_fft, size_t n, size_t ext, u
 // work_queue IFFT item (work_queue.hpp:272-276) for a wire whose Lagrange-base copy the prover keeps in `lagrange_copy`:
 // wire <- ifft(wire) in place, and the device mirror of lagrange_copy[0, n) is seeded from the data uploaded for the
 // transform (prover.cpp:184-186 memcpy'd it from `wire` just before), so round 3's grand product finds it on the device
-int bbg_wire_ifft(void* wire, size_t n, const void* lagrange_copy)
+int bbg_wire_ifft(void* wire, size_t n, const void* lagrange_copy, unsigned flags)
 {
     GET_CTX();
     StreamScope order(ctx, ctx->stream);
@@ -506,7 +506,7 @@ int bbg_wire_ifft(void* wire, size_t n, const void* lagrange_copy)
     }
     if ((rc = ntt_run_kind(ctx, args[0].d, n, BBG_IFFT, 0, nullptr, ctx->stream))) return rc;
     scope.tm.stop();
-    if ((rc = finish(ctx, args, 2, 0, ctx->stream, &d2h))) return rc;
+    if ((rc = finish(ctx, args, 2, flags, ctx->stream, &d2h))) return rc;
     scope.account(h2d, d2h);
     return scope.tm.finish();
 }

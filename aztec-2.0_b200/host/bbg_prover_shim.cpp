@@ -259,10 +259,13 @@ extern "C" void bbg_shim_process_queue(waffle::work_queue* self)
             polynomial& wire = witness->wires.at(item.tag);
             polynomial& wire_fft = key->wire_ffts.at(item.tag + "_fft");
             check(bbg_resident_invalidate(&wire_fft[0], wire_fft.get_max_size() * sizeof(fr)));
+            // ... and the wire itself: its mirror was left AHEAD of host memory by the previous proof (coefficients kept on the
+            // device), so the library would trust it over the witness the prover has just written
+            check(bbg_resident_invalidate(&wire[0], wire.get_max_size() * sizeof(fr)));
             // what polynomial::ifft does (polynomial.cpp:312-320), plus: the upload also seeds the mirror of the Lagrange
             // copy in wire_fft[0, n), which round 3's grand product reads
             if (n > wire.get_max_size()) wire.reserve(n);
-            check(bbg_wire_ifft(&wire[0], n, &wire_fft[0]));
+            check(bbg_wire_ifft(&wire[0], n, &wire_fft[0], defer ? BBG_KEEP_ON_DEVICE : 0));
             wire.resize_unsafe(n);
             ++i;
             break;
@@ -555,7 +558,16 @@ void ProverPermutationWidget<4, false, 4>::compute_round_commitments(transcript:
     fr blind[3];
     for (size_t k = 0; k < 3; ++k) blind[k] = fr::random_element();
     check(bbg_poly_write(&z[0], (n - 4) + 1, blind, 3));
-    z.ifft(key->small_domain); // device mirror -> coefficient form, written back: the CPU evaluates z in rounds 5 and 6
+    if (resident && turbo_key(key) && shim_enabled()) {
+        // coefficient form in the mirror only: the commitment, the coset FFT item of THIS file's process_queue (the
+        // reference's copies z on the host first), the opening evaluations and batch_open of a Turbo proof all read it
+        // there (polynomial::ifft's size bookkeeping, polynomial.cpp:312-320, by hand)
+        if (n > z.get_max_size()) z.reserve(n);
+        check(bbg_ntt_ex(&z[0], n, BBG_IFFT, 0, nullptr, BBG_KEEP_ON_DEVICE));
+        z.resize_unsafe(n);
+    } else {
+        z.ifft(key->small_domain);
+    }
     queue.add_to_queue({ work_queue::WorkType::SCALAR_MULTIPLICATION, z.get_coefficients(), "Z", fr(0), 0 });
     queue.add_to_queue({ work_queue::WorkType::FFT, nullptr, "z", fr(0), 0 });
 }

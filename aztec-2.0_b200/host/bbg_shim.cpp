@@ -163,7 +163,9 @@ void coset_fft_with_generator_shift(fr* coeffs, const evaluation_domain& domain,
 }
 void coset_ifft(fr* coeffs, const evaluation_domain& domain)
 {
-    check(bbg_ntt(coeffs, domain.size, BBG_COSET_IFFT, domain.generator_size, nullptr));
+    // the result stays in the array's device mirror only if the mirror is already ahead of host memory (the prover shim's
+    // quotient chain left it there: widgets -> divide_by_pseudo_vanishing_polynomial -> this transform -> commitments)
+    check(bbg_ntt_ex(coeffs, domain.size, BBG_COSET_IFFT, domain.generator_size, nullptr, BBG_KEEP_IF_AHEAD));
 }
 
 } // namespace polynomial_arithmetic

@@ -128,7 +128,7 @@ lib.bbg_peer_buffer_alloc.argtypes = [_sz, _vp, _vp]
 lib.bbg_peer_buffer_open.argtypes = [_vp, _vp]
 lib.bbg_peer_buffer_close.argtypes = [_vp]
 lib.bbg_peer_buffer_free.argtypes = [_vp]
-lib.bbg_wire_ifft.argtypes = [_vp, _sz, _vp]
+lib.bbg_wire_ifft.argtypes = [_vp, _sz, _vp, ctypes.c_uint]
 lib.bbg_evaluate_batch.argtypes = [_vp, _vp, _sz, _vp, _vp]
 lib.bbg_linear_combination.argtypes = [_vp, _vp, _vp, _vp, _sz, _sz, ctypes.c_uint]
 lib.bbg_resident_mode.argtypes = [_int]
@@ -655,8 +655,8 @@ def wire_coset_fft(wire, wire_fft, n, ext=4, flags=0):
     return wire_fft
 
 
-def wire_ifft(wire, lagrange_copy=None):
-    _check(lib.bbg_wire_ifft(wire.ctypes.data, wire.size // 4, None if lagrange_copy is None else lagrange_copy.ctypes.data))
+def wire_ifft(wire, lagrange_copy=None, flags=0):
+    _check(lib.bbg_wire_ifft(wire.ctypes.data, wire.size // 4, None if lagrange_copy is None else lagrange_copy.ctypes.data, flags))
     return wire
 
 

@@ -225,8 +225,9 @@ int bbg_wire_coset_fft(const void* wire, void* wire_fft, size_t n, size_t ext, u
 /* work_queue IFFT item (work_queue.hpp:272-276): wire <- ifft(wire), in place, n coefficients.  `lagrange_copy` (may be null):
  * a host array whose first n elements the caller has just copied from `wire` (prover.cpp:184-186 keeps the Lagrange-base
  * wires in w_i_fft[0, n) for the permutation widget); with resident polynomials its device mirror is seeded from the data
- * uploaded for the transform instead of being uploaded again in round 3. */
-int bbg_wire_ifft(void* wire, size_t n, const void* lagrange_copy);
+ * uploaded for the transform instead of being uploaded again in round 3.  flags: 0 or BBG_KEEP_ON_DEVICE (the coefficients
+ * stay in the wire's mirror: every later reader of a Turbo proof -- commitment, coset FFT, openings -- is a device step). */
+int bbg_wire_ifft(void* wire, size_t n, const void* lagrange_copy, unsigned flags);
 /* TransitionWidget::compute_quotient_contribution (bb/plonk/proof_system/widgets/transition_widgets/transition_widget.hpp:293-307)
  * for the TurboPLONK gate kernels: quotient[i] += identity(i) over the n_large-point coset domain.
  * polys: BBG_NUM_POLYNOMIALS pointers indexed like waffle::PolynomialIndex (types/polynomial_manifest.hpp:10-50) to the
