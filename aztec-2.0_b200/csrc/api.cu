@@ -764,7 +764,18 @@ static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, 
     cudaStream_t st[WAYS];
     st[0] = st0;
     for (int k = 1; k < WAYS; ++k) st[k] = ctx->aux_stream[k - 1];
-    const int used = (int)std::min<size_t>(count, WAYS);
+    // Small MSMs are FUSED, up to four per pass of the kernels (msm_device with an MsmBatch: the digits of vector m go to
+    // their own bucket sets, one sort / accumulate / merge / reduce chain for all of them): the latency-bound tail, which is
+    // most of a 2^16-point MSM, is paid once per group instead of once per MSM.  Large MSMs are throughput bound and keep
+    // one chain each; either way consecutive chains go to different streams and workspaces.
+    static const size_t fused_max = [] {
+        const char* v = getenv("BBG_MSM_FUSED_BATCH_MAX_LOG2"); // 0 disables fusing
+        const unsigned lg = v && *v ? (unsigned)atoi(v) : 17u;
+        return lg == 0 ? (size_t)0 : (size_t)1 << std::min(lg, 30u);
+    }();
+    const size_t group = (count > 1 && range > 0 && range <= fused_max) ? 4 : 1;
+    const size_t chains = (count + group - 1) / group;
+    const int used = (int)std::min<size_t>(chains, WAYS);
     if (used > 1) {
         BBG_CUDA(cudaEventRecord(ctx->ev_fork, st0));
         for (int k = 1; k < used; ++k) BBG_CUDA(cudaStreamWaitEvent(st[k], ctx->ev_fork, 0));
@@ -782,31 +793,43 @@ static int msm_batch(Context* ctx, PippengerObj* o, const void* const* scalars, 
         BBG_CUDA(cudaHostAlloc(&ctx->pinned, cap, cudaHostAllocDefault));
         ctx->pinned_cap = cap;
     }
-    for (size_t i = 0; i < count; ++i) {
-        MsmWorkspace& ws = ctx->msm_ws[i % WAYS];
-        cudaStream_t s = st[i % WAYS];
-        const void* d_sc = scalars[i];
-        if (!device_scalars) {
-            void* d_res = nullptr;
-            bool hit = false;
-            if (range && (rc = resident_acquire(ctx, scalars[i], range * 32, true, &d_res, &hit, s))) return rc;
-            if (d_res != nullptr) {
-                d_sc = d_res;
-                if (!hit) h2d += range * 32;
-            } else {
-                if ((rc = ws.scalars.reserve(std::max<size_t>(range, 1) * 32))) return rc;
-                if (range && (rc = g_staging.h2d(ws.scalars.p, scalars[i], range * 32, s))) return rc;
-                d_sc = ws.scalars.p;
-                h2d += range * 32;
+    for (size_t ch = 0; ch < chains; ++ch) {
+        MsmWorkspace& ws = ctx->msm_ws[ch % WAYS];
+        cudaStream_t s = st[ch % WAYS];
+        const size_t first = ch * group;
+        const size_t members = std::min(group, count - first);
+        MsmBatch mb;
+        mb.count = (unsigned)members;
+        for (auto& q : mb.scalars) q = nullptr;
+        if (!device_scalars && (rc = ws.scalars.reserve(std::max<size_t>(range, 1) * 32 * members))) return rc;
+        for (size_t m = 0; m < members; ++m) {
+            const size_t i = first + m;
+            const void* d_sc = scalars[i];
+            if (!device_scalars) {
+                void* d_res = nullptr;
+                bool hit = false;
+                if (range && (rc = resident_acquire(ctx, scalars[i], range * 32, true, &d_res, &hit, s))) return rc;
+                if (d_res != nullptr) {
+                    d_sc = d_res;
+                    if (!hit) h2d += range * 32;
+                } else {
+                    void* slot = (char*)ws.scalars.p + m * range * 32;
+                    if (range && (rc = g_staging.h2d(slot, scalars[i], range * 32, s))) return rc;
+                    d_sc = slot;
+                    h2d += range * 32;
+                }
             }
+            mb.scalars[m] = d_sc;
         }
-        void* d_out = device_results ? (char*)results + i * 96 : nullptr;
+        void* d_out = device_results ? (char*)results + first * 96 : nullptr;
         if (!device_results) {
-            if ((rc = ws.result.reserve(96))) return rc;
+            if ((rc = ws.result.reserve(96 * 4))) return rc;
             d_out = ws.result.p;
         }
-        if ((rc = msm_device(ctx, ws, d_sc, range, o->d_points, 1, o->lv, from, d_out, s, nullptr, /*allow_parts=*/used == 1))) return rc;
-        if (!device_results) BBG_CUDA(cudaMemcpyAsync((char*)ctx->pinned + i * 96, d_out, 96, cudaMemcpyDeviceToHost, s));
+        if ((rc = msm_device(ctx, ws, mb.scalars[0], range, o->d_points, 1, o->lv, from, d_out, s, nullptr, /*allow_parts=*/chains == 1,
+                             members > 1 ? &mb : nullptr)))
+            return rc;
+        if (!device_results) BBG_CUDA(cudaMemcpyAsync((char*)ctx->pinned + first * 96, d_out, 96 * members, cudaMemcpyDeviceToHost, s));
     }
     if (stat.row) stat.row->bytes_h2d += h2d;
     stat.h2d = h2d;

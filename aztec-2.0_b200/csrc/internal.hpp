@@ -39,9 +39,15 @@ struct MsmArrival {
     size_t count = 0;
     size_t piece = 0;
 };
+// fused batch: up to four scalar vectors (device pointers, n elements each) over the same bases and range in ONE pass of the
+// MSM kernels; d_out then receives `count` Jacobian results
+struct MsmBatch {
+    const void* scalars[4];
+    unsigned count;
+};
 int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, const void* d_points, size_t point_stride,
                const MsmLevels& lv, size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival = nullptr,
-               bool allow_parts = true);
+               bool allow_parts = true, const struct MsmBatch* batch = nullptr);
 int g1_sum_device(Context* ctx, const void* d_jacs, size_t n, void* d_out, cudaStream_t st);
 int srs_decode_device(Context* ctx, const void* d_raw, size_t n, void* d_points, cudaStream_t st);
 int point_table_device(Context* ctx, const void* d_points, size_t n, void* d_table, cudaStream_t st);

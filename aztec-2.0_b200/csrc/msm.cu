@@ -52,6 +52,8 @@ struct DigitParams {
     uint32_t level_stride; // table entries between consecutive levels
     uint32_t base;         // table entry of scalar 0 (Pippenger `from`)
     uint32_t agg_from;     // windows >= agg_from are narrow (few distinct digits): warp-aggregated counter updates
+    // fused batch: blockIdx.y = member; member m > 0 reads more[m - 1]; its windows go to bucket sets [m S, (m + 1) S)
+    const void* more[3];
 };
 
 // MODE 0: histogram of bucket sizes.  MODE 1: counting-sort scatter of schedule words (table index << 1 | negate).
@@ -71,6 +73,9 @@ __global__ void __launch_bounds__(256) k_msm_digits(const fr_t* __restrict__ sca
     // no early exit: every lane of a warp walks the (uniform) window loop so that the aggregated path below can name
     // the full warp in its *_sync primitives; lanes past the end carry an all-zero scalar and never touch memory
     const bool valid = i < P.n;
+    const uint32_t member = blockIdx.y;
+    if (member != 0) scalars = (const fr_t*)P.more[member - 1];
+    const uint32_t set_base = member * P.S;
     // from_montgomery_form => canonical integer in [0, r)  (scalar_multiplication.cpp:224)
     fr_t s = fe_zero<FrParams>();
     if (valid) s = fe_from_mont(fe_load_nc<FrParams>(scalars + i));
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const fr_t* __restrict__ sca
         uint32_t mag = neg ? (mask + 1 - v) : v;
         carry = neg;
         const bool live = valid && mag != 0;
-        const uint32_t g = set * P.B + (mag - 1);
+        const uint32_t g = (set_base + set) * P.B + (mag - 1);
         uint32_t dst = 0;
         if (w >= P.agg_from) {
             // The top window of a 254-bit scalar can be a few bits wide (c = 18: two bits): a million atomics on
@@ -913,7 +918,7 @@ static constexpr int FINISH_THREADS = 256; // 64 teams; more bucket sets than th
 //    stays in XYZZ for k_msm_parts_sum.
 __global__ void __launch_bounds__(FINISH_THREADS) k_msm_finish(const xyzz_t* __restrict__ level_sums, const ReduceRows rows, uint32_t c,
                                                                jac_t* __restrict__ out, uint32_t plain_level, uint32_t weight_offset,
-                                                               xyzz_t* __restrict__ out_xyzz)
+                                                               xyzz_t* __restrict__ out_xyzz, uint32_t members)
 {
     extern __shared__ xyzz_t sm_sets[]; // S entries
     const Team tm = team_of_lane();
@@ -941,28 +946,30 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_msm_finish(const xyzz_t* __r
         if (tm.r == 0) sm_sets[set] = v;
     }
     __syncthreads();
-    if (team != 0) {
+    // fused batch: the S sets are `members` groups of S / members; team m combines group m into out[m]
+    if (team >= members) {
         return;
     }
+    const uint32_t per = S / members;
     xyzz_t acc = xyzz_infinity();
-    for (int r = (int)S - 1; r >= 0; --r) {
-        if (r != (int)S - 1) {
+    for (int r = (int)per - 1; r >= 0; --r) {
+        if (r != (int)per - 1) {
             for (uint32_t d = 0; d < c; ++d) {
                 xyzz_dbl_team(tm, acc);
             }
         }
-        xyzz_t s = sm_sets[r];
+        xyzz_t s = sm_sets[team * per + r];
         xyzz_add_team(tm, acc, s);
     }
     if (tm.r == 0) {
         if (out_xyzz != nullptr) {
-            xyzz_store(out_xyzz, acc);
+            xyzz_store(out_xyzz + team, acc);
             return;
         }
         jac_t j = xyzz_to_jacobian(acc);
-        fe_store(&out->x, j.x);
-        fe_store(&out->y, j.y);
-        fe_store(&out->z, j.z);
+        fe_store(&out[team].x, j.x);
+        fe_store(&out[team].y, j.y);
+        fe_store(&out[team].z, j.z);
     }
 }
 
@@ -989,6 +996,7 @@ __global__ void __launch_bounds__(32) k_msm_parts_sum(const xyzz_t* __restrict__
 __global__ void k_set_infinity(jac_t* out)
 {
     jac_t j = xyzz_to_jacobian(xyzz_infinity());
+    out += blockIdx.x;
     fe_store(&out->x, j.x);
     fe_store(&out->y, j.y);
     fe_store(&out->z, j.z);
@@ -1216,12 +1224,19 @@ int msm_precompute_device(Context* ctx, void* d_table, size_t n, const MsmLevels
 // Device-pointer MSM over table entries [base, base + n) of level 0 (and the same range of every other level).
 //   lv.L == 1: plain points (any stride), W bucket sets.   lv.L > 1: fixed-base levels, S = D / c bucket sets.
 int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, const void* d_points, size_t point_stride,
-               const MsmLevels& lv_in, size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival, bool allow_parts)
+               const MsmLevels& lv_in, size_t base, void* d_out, cudaStream_t st, const MsmArrival* arrival, bool allow_parts,
+               const MsmBatch* batch)
 {
     Profiler& pr = ctx->prof;
     pr.begin();
+    const unsigned members = batch != nullptr ? batch->count : 1u;
+    if (members < 1 || members > 4) {
+        set_last_error("msm: a fused batch holds 1..4 scalar vectors");
+        return BBG_ERR_ARG;
+    }
+    if (batch != nullptr) d_scalars = batch->scalars[0];
     if (n == 0) {
-        k_set_infinity<<<1, 1, 0, st>>>((jac_t*)d_out);
+        k_set_infinity<<<members, 1, 0, st>>>((jac_t*)d_out);
         ctx->launches += 1;
         BBG_CUDA(cudaGetLastError());
         return BBG_OK;
@@ -1236,10 +1251,13 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
     }
     const unsigned c = lv.c;
     const unsigned W = (255 + c - 1) / c; // W*c >= 255: the top window absorbs the last carry
-    const unsigned S = lv.L == 1 ? W : lv.D / c;
+    // bucket sets: Sm per scalar vector; a fused batch of `members` vectors over the same bases is ONE pass of every kernel
+    // below over members * Sm sets (the digits of vector m go to sets [m Sm, (m + 1) Sm)), split again in k_msm_finish
+    const unsigned Sm = lv.L == 1 ? W : lv.D / c;
+    const unsigned S = Sm * members;
     const uint32_t B = 1u << (c - 1);
     const size_t G = (size_t)S * B;
-    const size_t max_entries = (size_t)W * n;
+    const size_t max_entries = (size_t)W * n * members;
     if (max_entries >= (1ull << 32) || ((size_t)(lv.L - 1) * lv.stride + base + n) >= (1ull << 31)) {
         set_last_error("msm: too many points for 32-bit schedule entries (shard the MSM by point range)");
         return BBG_ERR_ARG;
@@ -1266,7 +1284,8 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
     dp.n = (uint32_t)n;
     dp.c = c;
     dp.W = W;
-    dp.S = S;
+    dp.S = Sm;
+    for (unsigned m = 1; m < 4; ++m) dp.more[m - 1] = (batch != nullptr && m < members) ? batch->scalars[m] : nullptr;
     dp.B = B;
     dp.level_stride = (uint32_t)lv.stride;
     dp.base = (uint32_t)base;
@@ -1279,7 +1298,8 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
         }
     }
     dp.agg_from = env_uint("BBG_MSM_AGG_FROM", dp.agg_from);
-    const unsigned dig_blocks = div_up(n, 256);
+    const dim3 dig_blocks(div_up(n, 256), members);
+    if (batch != nullptr) arrival = nullptr;
     if (arrival != nullptr && arrival->count > 1) {
         // the histogram does not care which scalar a digit came from: count every piece as soon as its copy has landed
         for (size_t k = 0; k < arrival->count; ++k) {
@@ -1305,6 +1325,7 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
     // tested alternative (BBG_MSM_PAIR_PASSES = number of levels) for parts where the balance differs.
     unsigned J = env_uint("BBG_MSM_PAIR_PASSES", 0);
     if (J > 12) J = 12;
+    if (members > 1) J = 0;
     // optional: the counting sort moves the points themselves (64 B each) so that every later read streams
     const bool materialise = J > 0 && env_uint("BBG_MSM_MATERIALISE", 0) != 0;
 
@@ -1526,7 +1547,7 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
         }
         if (mark) pr.mark(s, PH_MSM_COMBINE);
         k_msm_finish<<<1, FINISH_THREADS, S * sizeof(xyzz_t), s>>>(sums, rp.rows, c, (jac_t*)d_out, rp.rows.levels, h * Bp,
-                                                                   H > 1 ? part_results + h : nullptr);
+                                                                   H > 1 ? part_results + h : nullptr, members);
         ctx->launches += 1;
         return BBG_OK;
     };

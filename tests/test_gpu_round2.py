@@ -88,6 +88,59 @@ def test_msm_batch_skewed_scalars_both_workspaces(bbg, orc, srs_mini):
     assert [orc.jac_to_buffer(g) for g in got] == [ea, eb, ea]
 
 
+@pytest.mark.parametrize("levels,c,k", [(0, 0, 9), (1, 9, 4), (2, 0, 6), (0, 12, 2)])
+def test_msm_fused_batch_groups_and_level_splits(bbg, orc, srs_mini, levels, c, k, monkeypatch):
+    """Small MSMs of one batch call are fused four at a time into ONE pass of the kernels (api.cu msm_batch, msm_device with
+    an MsmBatch): vector m's digits go to bucket sets [m S, (m + 1) S).  Every way of splitting windows into fixed-base
+    levels x bucket sets (S = 1, S > 1, no precomputed levels at all), full and partial groups, zero and one-point ranges,
+    and a vector that is all zeros next to live ones must give the single-call results."""
+    pts, _ = srs_mini
+    if levels:
+        monkeypatch.setenv("BBG_MSM_LEVELS", str(levels))
+    if c:
+        monkeypatch.setenv("BBG_MSM_C", str(c))
+    pip = bbg.Pippenger.from_points(pts)
+    n = 2500
+    arrays = [inputs.fr_elements(900 + i, n, coarse_fraction=0.3 if i % 3 == 0 else 0.0) for i in range(k)]
+    arrays[1] = np.zeros((n, 4), dtype=np.uint64)  # all-zero scalars: the point at infinity
+    got = pip.pippenger_unsafe_batch(arrays, 7, n)
+    for i in range(k):
+        assert orc.jac_to_buffer(got[i]) == orc.jac_to_buffer(orc.pippenger(arrays[i], pts[7:7 + n], stride=1)), i
+    one = pip.pippenger_unsafe_batch([a[:1] for a in arrays], 3, 1)
+    for i in range(k):
+        assert orc.jac_to_buffer(one[i]) == orc.jac_to_buffer(orc.pippenger(arrays[i][:1], pts[3:4], stride=1)), i
+    none = pip.pippenger_unsafe_batch([a[:0] for a in arrays], 0, 0)
+    inf = orc.jac_to_buffer(orc.pippenger(arrays[0][:0], pts[:0], stride=1))
+    assert all(orc.jac_to_buffer(g) == inf for g in none)
+
+
+def test_msm_fused_batch_can_be_disabled(bbg, orc, srs_mini):
+    """BBG_MSM_FUSED_BATCH_MAX_LOG2 is read once per process: the un-fused batch path (one chain per MSM on four streams,
+    what large MSMs use) is exercised in a child process on the same inputs."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys\n"
+        "sys.path[:0] = ['.', 'tests', 'aztec-2.0_b200/python']\n"
+        "import numpy as np, bbg, inputs\n"
+        "from oracle import pyoracle as po\n"
+        "bbg.init(0)\n"
+        "orc = po.Oracle()\n"
+        "n = inputs.SRS_MINI_POINTS\n"
+        "pts = orc.read_transcript_g1(n, inputs.SRS_MINI_DIR)\n"
+        "pip = bbg.Pippenger.from_path(inputs.SRS_MINI_DIR, n)\n"
+        "arrays = [inputs.fr_elements(950 + i, n) for i in range(6)]\n"
+        "got = pip.pippenger_unsafe_batch(arrays, 0, n)\n"
+        "ok = all(orc.jac_to_buffer(got[i]) == orc.jac_to_buffer(orc.pippenger(arrays[i], pts, stride=1)) for i in range(6))\n"
+        "print('OK' if ok else 'MISMATCH')\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BBG_MSM_FUSED_BATCH_MAX_LOG2="0")
+    r = subprocess.run([sys.executable, "-c", code.replace("\\n", "\n")], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-500:] + r.stderr[-2000:]
+
+
 # ------------------------------------------------------------------------------------------ tiny / unregistered MSMs
 # bb/plonk/proof_system/verifier/verifier.cpp:164-170 calls pippenger with a few dozen points
 @pytest.mark.parametrize("n", [1, 2, 7, 27, 33, 255, 256, 257])
