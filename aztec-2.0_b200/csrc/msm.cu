@@ -1249,6 +1249,34 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
         lv.c = env_uint("BBG_MSM_C1", (unsigned)std::max(8, std::min(16, (int)floor_log2(n) - 4)));
         lv.stride = 0;
     }
+    if (lv.L > 1 && env_uint("BBG_MSM_CALL_WINDOW", 1) != 0) {
+        // A range much shorter than the object was built for (Pippenger::pippenger_unsafe(scalars, from, range) over a
+        // piece of a large SRS): the object's window would leave 2^(c-1) mostly empty buckets to reduce.  The levels are
+        // 2^(D l) P, so any c' = D / k works with k bucket sets per level (set s carries weight 2^(c' s), applied by
+        // k_msm_finish): take the k with the least arithmetic, in fq multiplies: W n x 10 (mixed additions) + 2 x 14 per bucket.
+        // Measured on a 2^20-point object (D = 20; ms with c = 20 -> c = 10, two sets): 2^12 points 0.94 -> 0.40, 2^14 0.90 ->
+        // 0.51, but 2^16 0.91 -> 1.10: with ~1 700 digits per bucket the histogram / scatter atomics pile up on 1 024 counters
+        // and every bucket is cut by dozens of chunks, so the switch is limited to <= 600 digits per bucket.
+        auto cost = [&](unsigned cc) {
+            const double Wc = (double)((255 + cc - 1) / cc);
+            return Wc * (double)n * 10.0 + (double)(lv.D / cc) * (double)(1ull << (cc - 1)) * 28.0;
+        };
+        unsigned best_c = lv.c;
+        double best = cost(lv.c);
+        for (unsigned k = 2; k <= 4; ++k) {
+            if (lv.D % k != 0) continue;
+            const unsigned c2 = lv.D / k;
+            if (c2 < 6 || c2 >= lv.c || lv.c % c2 != 0) continue;
+            const unsigned W2 = (255 + c2 - 1) / c2, S2 = lv.D / c2;
+            if ((W2 + S2 - 1) / S2 > lv.L) continue; // the narrower windows would reach past the last level
+            if ((double)W2 * (double)n > 600.0 * (double)S2 * (double)(1ull << (c2 - 1))) continue;
+            if (cost(c2) * 1.15 < best) {
+                best = cost(c2);
+                best_c = c2;
+            }
+        }
+        lv.c = best_c;
+    }
     const unsigned c = lv.c;
     const unsigned W = (255 + c - 1) / c; // W*c >= 255: the top window absorbs the last carry
     // bucket sets: Sm per scalar vector; a fused batch of `members` vectors over the same bases is ONE pass of every kernel

@@ -858,6 +858,8 @@ def prover_record(reps_gpu=6, reps_cpu=3):
         out[name] = rec
     try:
         out["speedup_vs_cpu"] = out["js_prover_cpu"]["construct_proof_ms"] / out["js_prover_gpu"]["construct_proof_ms"]
+        l1, full = out["js_prover_gpu_l1"]["pcie_bytes_per_proof"], out["js_prover_gpu"]["pcie_bytes_per_proof"]
+        out["pcie_bytes_per_proof_l1_over_resident"] = (l1["h2d"] + l1["d2h"]) / max(1, full["h2d"] + full["d2h"])
     except Exception:
         pass
     return out

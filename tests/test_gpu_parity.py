@@ -368,6 +368,27 @@ def test_msm_fixed_base_levels(bbg, orc, srs_mini, levels, c, monkeypatch):
     assert orc.jac_to_buffer(pip.pippenger_unsafe(one, 0, n)) == orc.jac_to_buffer(orc.pippenger(one, pts[:n], stride=1))
 
 
+@pytest.mark.parametrize("c", [12, 16, 18, 20])
+def test_msm_short_range_on_large_object_subdivides_windows(bbg, orc, srs_mini, c, monkeypatch):
+    """Pippenger::pippenger_unsafe(scalars, from, range) with a range far below the size the object's window was chosen
+    for: msm_device narrows the window to D / k (k bucket sets per fixed-base level) at call time.  Ranges on both sides of
+    the switch, against the oracle; BBG_MSM_CALL_WINDOW=0 (the object's own window) must give the same points."""
+    pts, table = srs_mini
+    monkeypatch.setenv("BBG_MSM_C", str(c))
+    pip = bbg.Pippenger.from_points(pts)
+    for frm, rng in ((0, 4096), (11, 700), (100, 64), (5, 9), (0, 1)):
+        sc = inputs.fr_elements(2100 + c + rng, rng, coarse_fraction=0.2)
+        exp = orc.jac_to_buffer(orc.pippenger(sc, pts[frm:frm + rng], stride=1))
+        assert orc.jac_to_buffer(pip.pippenger_unsafe(sc, frm, rng)) == exp, (c, frm, rng)
+        monkeypatch.setenv("BBG_MSM_CALL_WINDOW", "0")
+        assert orc.jac_to_buffer(pip.pippenger_unsafe(sc, frm, rng)) == exp, (c, frm, rng)
+        monkeypatch.delenv("BBG_MSM_CALL_WINDOW")
+    batch = [inputs.fr_elements(2200 + i, 300) for i in range(3)]
+    got = pip.pippenger_unsafe_batch(batch, 40, 300)
+    for i in range(3):
+        assert orc.jac_to_buffer(got[i]) == orc.jac_to_buffer(orc.pippenger(batch[i], pts[40:340], stride=1))
+
+
 @pytest.mark.parametrize("parts,c", [(2, 14), (4, 15), (2, 16), (4, 14), (1, 14)])
 def test_msm_bucket_range_parts(bbg, orc, srs_mini, parts, c, monkeypatch):
     """msm.cu "parts": one bucket set cut into contiguous bucket ranges, each with its own accumulate -> merge -> reduce
