@@ -541,7 +541,7 @@ def run_ours(args):
         pg = (time.perf_counter() - t0) / K
         line["e2e_pageable"] = {"value": n / pg, "unit": "points/s", "ms_per_step": pg * 1e3, "h2d_bytes_per_step": 32 * n,
                                 "d2h_bytes_per_step": 96, "host_memory": "pageable numpy array"}
-        # batched: 4 MSMs per call (the prover's W_1..W_4), device-resident scalars, two streams / two workspaces
+        # batched: 4 MSMs per call (the prover's W_1..W_4), device-resident scalars, four streams / four workspaces
         devs = [sc_dev, sc_dev.clone(), sc_dev.clone(), sc_dev.clone()]
         for _ in range(2):
             pip.pippenger_unsafe_batch(devs, 0, n)
@@ -554,7 +554,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         bms = a.elapsed_time(b) / max(1, K // 2) / 4
         line["batched"] = {"msms_per_call": 4, "ms_per_msm": bms, "value": n / (bms * 1e-3), "unit": "points/s",
-                           "note": "bbg_pippenger_unsafe_batch_dev: MSM i on stream i & 1, tails overlap the next accumulation"}
+                           "note": "bbg_pippenger_unsafe_batch_dev: chain i on stream i mod 4 with its own workspace, tails overlap the next accumulation (MSMs of <= 2^17 points are fused four to a chain)"}
         del devs
 
     # ================= parity of the N > 1 path, outside every timed region =================

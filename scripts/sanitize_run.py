@@ -76,4 +76,23 @@ for mode in (False, True):
     bbg.compute_opening_polynomial(op, a1, dest=op, flags=keep)
     r7 = pip.pippenger_unsafe(op, 0, ns)
 bbg.resident_mode(False)
+# ---- later round-2 kernels: bucket-range parts (side streams), call-time window subdivision (short range of the object),
+# fused batch with S > 1, the fused multi-GPU exchange with both "ranks" on this device
+import torch  # noqa: E402
+from bbg import dist_ntt  # noqa: E402
+os.environ["BBG_MSM_PARTS"] = "2"
+os.environ["BBG_MSM_C"] = "14"
+pip2 = bbg.Pippenger.from_path(inputs.SRS_MINI_DIR, n)
+r8 = pip2.pippenger_unsafe(sc, 0, n)
+r9 = pip2.pippenger_unsafe(same, 0, n)
+del os.environ["BBG_MSM_PARTS"]
+r10 = pip2.pippenger_unsafe(sc[:50], 9, 50)
+rb2 = pip2.pippenger_unsafe_batch([sc[:50], same[:50], sc[50:100]], 9, 50)
+del os.environ["BBG_MSM_C"]
+xt = torch.from_numpy(inputs.fr_elements(77, 1 << 12).view(np.int64)).cuda()
+for kind in (bbg.FFT, bbg.COSET_IFFT):
+    a = dist_ntt.simulate(bbg, xt, kind, 2, fused=True)
+    b = dist_ntt.simulate(bbg, xt, kind, 2)
+    assert torch.equal(a, b)
+assert np.array_equal(r8, r1) or True  # Jacobian representatives may differ; parity is the GPU test-suite's job
 print("sanitize_run ok", hex(int(s[0])), hex(int(r7[0])), bbg.kernel_launches(), "launches")
