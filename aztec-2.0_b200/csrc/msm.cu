@@ -642,10 +642,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2) k_msm_pair_pass(const uint32_
 // A worker is a TEAM of four lanes (g1_team.cuh): the chain of up to MERGE_K - 1 additions per level is what this phase
 // costs, and there are far fewer workers than lanes.  All lanes of a team read the same slots and take the same branches;
 // lane 0 writes.
+// TEAM = false: the worker is ONE thread with plain additions -- level 0 of a large MSM has ~57 k workers with ~7 additions
+// each, i.e. it is throughput bound, and the cooperative form spends 16 multiplies of four lanes where 14 of one do.
+template <bool TEAM = true>
 __device__ __forceinline__ void merge_worker(const Team& tm, const Slot* __restrict__ in, uint32_t n_in, uint32_t workers, uint32_t u,
                                              xyzz_t* __restrict__ buckets, Slot* __restrict__ out, uint32_t* __restrict__ pending_out)
 {
-    const bool writer = tm.r == 0;
+    const bool writer = !TEAM || tm.r == 0;
     const uint32_t lo = u == 0 ? 0 : u * MERGE_K + 1;
     uint32_t hi = (u + 1) * MERGE_K + 1;
     if (hi > n_in || u + 1 == workers) hi = n_in;
@@ -683,7 +686,12 @@ __device__ __forceinline__ void merge_worker(const Team& tm, const Slot* __restr
                 run_start = i;
                 acc = x;
             } else {
-                xyzz_add_team(tm, acc, x); // the one inlined add site of this kernel
+                // the one inlined add site of this kernel
+                if constexpr (TEAM) {
+                    xyzz_add_team(tm, acc, x);
+                } else {
+                    xyzz_add(acc, x);
+                }
             }
         }
     }
@@ -697,6 +705,7 @@ __device__ __forceinline__ void merge_worker(const Team& tm, const Slot* __restr
 }
 
 // levels 0-2: one team per worker over the slots the level before left
+template <bool TEAM>
 __global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
                                                     uint32_t n_in,
                                                     uint32_t workers,
@@ -709,11 +718,12 @@ __global__ void __launch_bounds__(128) k_msm_merge(const Slot* __restrict__ in,
         return; // nothing was left open
     }
     const Team tm = team_of_lane();
-    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t u = TEAM ? gtid >> 2 : gtid;
     if (u >= workers) {
         return; // team-uniform
     }
-    merge_worker(tm, in, n_in, workers, u, buckets, out, pending_out);
+    merge_worker<TEAM>(tm, in, n_in, workers, u, buckets, out, pending_out);
 }
 
 // Levels 0-2 are ordinary grid-wide launches of k_msm_merge (each exits at once when the level before left nothing
@@ -1523,8 +1533,14 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
                 const size_t workers = n_in > 1 ? (n_in - 1 + MERGE_K - 1) / MERGE_K : 1;
                 Slot* out = in + n_in;
                 if (level < MERGE_GRID_LEVELS) {
-                    k_msm_merge<<<div_up(workers * 4, 128), 128, 0, s>>>(in, (uint32_t)n_in, (uint32_t)workers, pend + level, buckets, out,
-                                                                        pend + level + 1);
+                    // many workers (level 0 of >= 2^18 points: ~57 k): throughput bound, one thread each; else a team each
+                    if (workers >= env_uint("BBG_MSM_MERGE_WIDE_FROM", 32768)) {
+                        k_msm_merge<false><<<div_up(workers, 128), 128, 0, s>>>(in, (uint32_t)n_in, (uint32_t)workers, pend + level, buckets, out,
+                                                                               pend + level + 1);
+                    } else {
+                        k_msm_merge<true><<<div_up(workers * 4, 128), 128, 0, s>>>(in, (uint32_t)n_in, (uint32_t)workers, pend + level, buckets, out,
+                                                                                  pend + level + 1);
+                    }
                     ctx->launches += 1;
                 } else {
                     k_msm_merge_rest<<<1, MERGE_REST_THREADS, 0, s>>>(in, (uint32_t)n_in, level, pend, buckets);

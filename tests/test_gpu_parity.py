@@ -368,6 +368,25 @@ def test_msm_fixed_base_levels(bbg, orc, srs_mini, levels, c, monkeypatch):
     assert orc.jac_to_buffer(pip.pippenger_unsafe(one, 0, n)) == orc.jac_to_buffer(orc.pippenger(one, pts[:n], stride=1))
 
 
+@pytest.mark.parametrize("wide_from", [1, 100, 10 ** 9])
+def test_msm_slot_merge_wide_and_team_workers(bbg, orc, srs_mini, wide_from, monkeypatch):
+    """k_msm_merge<TEAM>: a merge level with many workers runs one thread per worker (plain additions), otherwise a team of
+    four lanes per worker; BBG_MSM_MERGE_WIDE_FROM moves the switch so that both forms see every level on uniform, skewed
+    (all digits in one bucket: every level has work) and mixed inputs."""
+    pts, table = srs_mini
+    monkeypatch.setenv("BBG_MSM_MERGE_WIDE_FROM", str(wide_from))
+    pip = bbg.Pippenger.from_points(pts)
+    n = inputs.SRS_MINI_POINTS
+    sc = inputs.fr_elements(2300, n, coarse_fraction=0.3)
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(sc, 0, n)) == orc.jac_to_buffer(orc.pippenger(sc, pts[:n], stride=1))
+    one = np.repeat(inputs.fr_elements(8, 1), n, axis=0)
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(one, 0, n)) == orc.jac_to_buffer(orc.pippenger(one, pts[:n], stride=1))
+    two = one.copy()
+    two[::2] = inputs.fr_elements(9, 1)
+    assert orc.jac_to_buffer(pip.pippenger_unsafe(two, 0, n)) == orc.jac_to_buffer(orc.pippenger(two, pts[:n], stride=1))
+    assert orc.jac_to_buffer(bbg.msm_points(sc[:777], pts[:777])) == orc.jac_to_buffer(orc.pippenger(sc[:777], pts[:777], stride=1))
+
+
 @pytest.mark.parametrize("c", [12, 16, 18, 20])
 def test_msm_short_range_on_large_object_subdivides_windows(bbg, orc, srs_mini, c, monkeypatch):
     """Pippenger::pippenger_unsafe(scalars, from, range) with a range far below the size the object's window was chosen
