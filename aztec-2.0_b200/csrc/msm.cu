@@ -864,7 +864,7 @@ struct ReduceRows {
     uint32_t levels;
     uint32_t off[REDUCE_MAX_LEVELS]; // entry offset of level l's R array (set-major, m[l] per set)
     uint32_t m[REDUCE_MAX_LEVELS];
-    uint32_t shift[REDUCE_MAX_LEVELS]; // log2(ell) of level l
+    uint32_t mult[REDUCE_MAX_LEVELS];  // ell of level l (segment length: the factor between level l + 1 and level l); any integer >= 1
 };
 
 // lane-to-lane move of a whole point between TEAMS of one warp (delta in lanes, a multiple of 4)
@@ -938,8 +938,14 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_msm_finish(const xyzz_t* __r
         // Horner from the deepest level
         xyzz_t v = xyzz_infinity();
         for (int level = (int)rows.levels - 1; level >= 0; --level) {
-            for (uint32_t d = 0; d < rows.shift[level] && level != (int)rows.levels - 1; ++d) {
-                xyzz_dbl_team(tm, v);
+            if (level != (int)rows.levels - 1 && rows.mult[level] > 1) {
+                // v *= ell (double-and-add; a power of two is doublings only)
+                const uint32_t k = rows.mult[level];
+                const xyzz_t base = v;
+                for (int bit = 30 - __clz(k); bit >= 0; --bit) {
+                    xyzz_dbl_team(tm, v);
+                    if ((k >> bit) & 1) xyzz_add_team(tm, v, base);
+                }
             }
             xyzz_t r = xyzz_load(level_sums + (size_t)level * S + set);
             xyzz_add_team(tm, v, r);
@@ -1466,7 +1472,7 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
     struct ReducePlan {
         ReduceRows rows;
         uint32_t segs0, count1, segs1, parts;
-        unsigned sh0, sh1;
+        unsigned ell0, sh1;
         bool team0;
         size_t total_segs, n_rows, elems;
     };
@@ -1476,21 +1482,26 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
         // Measured on B200, 2^19 buckets (ms of bucket reduction; round 1's shape ell0 = 16, ell1 = 4 with plain additions: 0.65):
         // teams at both levels 16/4: 0.65, 4/16: 0.77; plain level 0 + team level 1: 4/8 0.61, 4/16 0.53, 4/32 0.58,
         // 8/8 0.51, 8/16 0.53, 2/16 0.73.  Small bucket sets (2^15 buckets, c = 16): teams at both levels, 4/4: 0.18 (0.34).
+        // A later sweep with arbitrary (non power-of-two) ell0 -- 6, 10, 12 at 2^19 buckets; 3, 5, 6 at 2^17; 2, 3, 6 at 2^15 --
+        // and a 128-register / four-CTA build of level 0 moved the whole MSM by less than 1.5 % either way: level 0 is bound by
+        // its multiplies (2 full additions per bucket), not by wave quantisation.
         ReducePlan rp;
         const bool big = nb >= (1u << 17);
-        rp.sh0 = std::min(6u, env_uint("BBG_MSM_ELL0_LOG2", big ? 3u : 2u));
+        // ell0 need not be a power of two (k_msm_finish multiplies by it with a double-and-add): BBG_MSM_ELL0 = any length
+        rp.ell0 = 1u << std::min(6u, env_uint("BBG_MSM_ELL0_LOG2", big ? 3u : 2u));
+        rp.ell0 = std::max(1u, std::min(64u, env_uint("BBG_MSM_ELL0", rp.ell0)));
         rp.sh1 = std::min(6u, env_uint("BBG_MSM_ELL1_LOG2", big ? 3u : 2u));
-        rp.team0 = env_uint("BBG_MSM_SEG0_TEAM", ((size_t)S * (nb >> rp.sh0)) < (1u << 16) ? 1u : 0u) != 0;
+        rp.team0 = env_uint("BBG_MSM_SEG0_TEAM", ((size_t)S * (nb / rp.ell0)) < (1u << 16) ? 1u : 0u) != 0;
         memset(&rp.rows, 0, sizeof(rp.rows));
         rp.rows.S = (uint32_t)S;
-        rp.segs0 = (nb + (1u << rp.sh0) - 1) >> rp.sh0;
+        rp.segs0 = (nb + rp.ell0 - 1) / rp.ell0;
         rp.count1 = rp.segs0 - 1; // level 1 works on T[1..]
         rp.segs1 = (rp.count1 + (1u << rp.sh1) - 1) >> rp.sh1;
         rp.rows.levels = rp.count1 ? 2 : 1;
-        rp.rows.shift[0] = rp.sh0;
+        rp.rows.mult[0] = rp.ell0;
         rp.rows.m[0] = rp.segs0;
         rp.rows.off[0] = 0;
-        rp.rows.shift[1] = rp.sh1;
+        rp.rows.mult[1] = 1u << rp.sh1;
         rp.rows.m[1] = rp.segs1;
         rp.rows.off[1] = (uint32_t)((size_t)rp.segs0 * S);
         rp.total_segs = (size_t)rp.segs0 + rp.segs1;
@@ -1562,9 +1573,9 @@ int msm_device(Context* ctx, MsmWorkspace& ws, const void* d_scalars, size_t n, 
         {
             const uint32_t workers = rp.segs0 * (uint32_t)S;
             if (rp.team0) {
-                k_msm_segments<false, true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, s>>>(bk, Bp, Bp, 1u << rp.sh0, rp.segs0, workers, r_all, t0);
+                k_msm_segments<false, true><<<div_up((size_t)workers * 4, SEG_THREADS), SEG_THREADS, 0, s>>>(bk, Bp, Bp, rp.ell0, rp.segs0, workers, r_all, t0);
             } else {
-                k_msm_segments<false, false><<<div_up(workers, SEG_THREADS), SEG_THREADS, 0, s>>>(bk, Bp, Bp, 1u << rp.sh0, rp.segs0, workers, r_all, t0);
+                k_msm_segments<false, false><<<div_up(workers, SEG_THREADS), SEG_THREADS, 0, s>>>(bk, Bp, Bp, rp.ell0, rp.segs0, workers, r_all, t0);
             }
             ctx->launches += 1;
         }
