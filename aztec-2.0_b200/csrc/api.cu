@@ -1188,6 +1188,42 @@ int bbg_ntt_dist_fused_dev(const void* d_src, void* d_work, void* const* peer_re
     return ntt_device(ctx, d_src, d_work, lg, inverse, pro, epi, 0, 0, (cudaStream_t)stream, dist);
 }
 
+// The multi-GPU transform on NATURAL contiguous blocks (rank q holds x[q n / W, (q + 1) n / W) and ends with
+// X[q n / W, (q + 1) n / W)), entirely over peer memory: phase 0 loads its sliced sub-array from the owners' input blocks
+// in its first pass and stores into the owners' receive buffers in its last; phase 1 transforms the own receive buffer and
+// stores every output to the owner of its natural index.  No all-to-all, no re-distribution.  The caller orders the phases
+// across ranks (a stream-ordered one-word all-reduce each): inputs written -> phase 0 -> phase 1 -> outputs readable.
+int bbg_ntt_dist_natural_dev(void* const* peer_in, void* d_work, void* const* peer_recv, void* const* peer_out, size_t n, int kind,
+                             size_t generator_size, const void* constant, int rank, int world, int phase, void* stream)
+{
+    GET_CTX();
+    StreamScope order(ctx, (cudaStream_t)stream);
+    unsigned lg;
+    int rc = log2_exact(n, lg);
+    if (rc) return rc;
+    unsigned ip, op;
+    if ((rc = bbg_ntt_dist_layout(n, world, &ip, &op))) return rc;
+    if (rank < 0 || rank >= world || world < 2 || world > 8 || (phase != 0 && phase != 1) || peer_recv == nullptr ||
+        (phase == 0 && (peer_in == nullptr || d_work == nullptr)) || (phase == 1 && peer_out == nullptr)) {
+        set_last_error("ntt_dist_natural: 2..8 ranks, phase 0 (peer_in, d_work, peer_recv) or 1 (peer_recv, peer_out)");
+        return BBG_ERR_ARG;
+    }
+    bool inverse;
+    NttScale pro, epi;
+    if ((rc = ntt_kind_params(kind, lg, generator_size, constant, inverse, pro, epi))) return rc;
+    NttDist dist;
+    dist.rank = (unsigned)rank;
+    dist.phase = phase;
+    while ((1 << dist.rank_bits) < world) ++dist.rank_bits;
+    if (phase == 0) {
+        dist.peer_src = peer_in;
+        dist.peer_recv = peer_recv;
+        return ntt_device(ctx, peer_in[rank], d_work, lg, inverse, pro, epi, 0, 0, (cudaStream_t)stream, dist);
+    }
+    dist.peer_out = peer_out;
+    return ntt_device(ctx, peer_recv[rank], peer_out[rank], lg, inverse, pro, epi, 0, 0, (cudaStream_t)stream, dist);
+}
+
 // ---- peer-mapped buffers (CUDA IPC): memory another rank's kernels can store into over NVLink
 int bbg_peer_buffer_alloc(size_t bytes, void** d_ptr, void* ipc_handle64)
 {

@@ -84,6 +84,10 @@ struct NttDist {
     unsigned rank = 0;
     int phase = 0;          // 0: every pass but the last (before the all-to-all); 1: the last pass (after it)
     void* const* peer_recv = nullptr; // phase 0, fused exchange: receive buffer of every rank (peer-mapped); null = local store + NCCL
+    // natural block distribution over peer memory: phase 0's first pass loads from the owners' input blocks, phase 1's pass
+    // stores to the owners' output blocks (each block n / world elements); null = the packed sliced layouts
+    void* const* peer_src = nullptr;
+    void* const* peer_out = nullptr;
 };
 int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, bool inverse, const NttScale& pro, const NttScale& epi,
                unsigned out_shift, unsigned out_off, cudaStream_t st, const NttDist& dist = NttDist());

@@ -118,6 +118,12 @@ struct PassParams {
     // (rk_val << chunk_log) + (a & chunk mask) of that rank's buffer -- exactly where the all-to-all would have put it.
     uint32_t peer_on;
     fr* peer_dst[8];
+    // Natural block distribution over peer memory (rank q holds elements [q << block_log, (q + 1) << block_log) of the
+    // input / output array): the FIRST pass loads element `at` (true coefficient index) from peer_src[at >> block_log],
+    // the LAST pass stores output o to peer_out[o >> block_log] -- no re-distribution step on either side.
+    uint32_t src_on, out_on, block_log;
+    const fr* peer_src[8];
+    fr* peer_out[8];
 };
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return __brev(x) >> (32 - bits); }
@@ -354,6 +360,14 @@ __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams
             mid = tile >> o1_bits;
         }
     };
+    // where element `a` of this rank's packed input lives: locally, or (natural blocks over peer memory) with its owner
+    auto first_pass_src = [&](uint32_t a) -> const fr* {
+        if (P.src_on) {
+            const uint32_t at = (uint32_t)insert_bits(a, P.rk_pos, P.rk_bits, P.rk_val); // true coefficient index
+            return P.peer_src[at >> P.block_log] + (at & ((1u << P.block_log) - 1u));
+        }
+        return P.src + a;
+    };
     // PERSIST: start the copies of tile group `grp` into the staging area
     auto prefetch = [&](uint32_t grp) {
         const uint32_t t = grp * tiles_per_cta + tile_local;
@@ -364,7 +378,7 @@ __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
                     const uint32_t row = (uint32_t)j * rows8 + q;
-                    const uint4* src = reinterpret_cast<const uint4*>(P.src + (ib + (row << P.below) + col));
+                    const uint4* src = reinterpret_cast<const uint4*>(first_pass_src(ib + (row << P.below) + col));
                     cp_async16(stage + (2 * j) * NTT_THREADS + threadIdx.x, src);
                     cp_async16(stage + (2 * j + 1) * NTT_THREADS + threadIdx.x, src + 1);
                 }
@@ -444,7 +458,7 @@ __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams
             for (int j = 0; j < E; ++j) {
                 const uint32_t row = (uint32_t)j * rows8 + q;
                 const uint32_t a = in_base + (row << P.below) + col;
-                x[j] = fe_load<FrParams>(P.src + a);
+                x[j] = fe_load<FrParams>(first_pass_src(a));
                 pre_scale(x[j], a);
             }
         }
@@ -566,8 +580,12 @@ __global__ void __launch_bounds__(NTT_THREADS, CTAS) k_ntt_pass(const PassParams
             } else if (P.epi_mode == 3) {
                 x[j] = fe_mul(x[j], fe_load_nc<FrParams>(P.epi_full + o));
             }
-            const uint32_t ol = P.rk_bits ? (uint32_t)squeeze_bits(o, P.g1, P.rk_bits) : o; // local slot of natural index o
-            fe_store(P.dst + (((size_t)ol << P.out_shift) + P.out_off), x[j]);
+            if (P.out_on) {
+                fe_store(P.peer_out[o >> P.block_log] + (o & ((1u << P.block_log) - 1u)), x[j]); // the owner of natural index o
+            } else {
+                const uint32_t ol = P.rk_bits ? (uint32_t)squeeze_bits(o, P.g1, P.rk_bits) : o; // local slot of natural index o
+                fe_store(P.dst + (((size_t)ol << P.out_shift) + P.out_off), x[j]);
+            }
         }
     }
     } // active
@@ -1071,6 +1089,18 @@ int ntt_device(Context* ctx, const void* d_src, void* d_dst, unsigned log_n, boo
         if (rb > 0 && dist.peer_recv != nullptr && dist.phase == 0 && p + 2 == num_passes) {
             pp.peer_on = 1;
             for (unsigned r = 0; r < (1u << rb); ++r) pp.peer_dst[r] = (fr*)dist.peer_recv[r];
+        }
+        pp.src_on = pp.out_on = 0;
+        pp.block_log = log_local;
+        for (auto& q : pp.peer_src) q = nullptr;
+        for (auto& q : pp.peer_out) q = nullptr;
+        if (rb > 0 && dist.peer_src != nullptr && dist.phase == 0 && p == 0) {
+            pp.src_on = 1;
+            for (unsigned r = 0; r < (1u << rb); ++r) pp.peer_src[r] = (const fr*)dist.peer_src[r];
+        }
+        if (rb > 0 && dist.peer_out != nullptr && dist.phase == 1 && last) {
+            pp.out_on = 1;
+            for (unsigned r = 0; r < (1u << rb); ++r) pp.peer_out[r] = (fr*)dist.peer_out[r];
         }
         pp.pro_lo = (p == 0) ? pro_lo : nullptr;
         pp.pro_hi = (p == 0) ? pro_hi : nullptr;

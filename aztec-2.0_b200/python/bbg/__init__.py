@@ -37,7 +37,7 @@ EXPORTS = [
     "bbg_pippenger_unsafe_batch", "bbg_pippenger_unsafe_batch_dev", "bbg_pippenger_batch",
     "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_ntt_ex", "bbg_wire_coset_fft", "bbg_turbo_quotient",
     "bbg_permutation_quotient", "bbg_divide_by_pseudo_vanishing_polynomial", "bbg_compute_lagrange_polynomial_fft",
-    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_wire_ifft", "bbg_stats_totals", "bbg_ntt_dist_fused_dev",
+    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_wire_ifft", "bbg_stats_totals", "bbg_ntt_dist_fused_dev", "bbg_ntt_dist_natural_dev",
     "bbg_peer_buffer_alloc", "bbg_peer_buffer_open", "bbg_peer_buffer_close", "bbg_peer_buffer_free", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
 ]
 
@@ -124,6 +124,7 @@ lib.bbg_compute_opening_polynomial.argtypes = [_vp, _vp, _vp, _sz, _sz, _vp, cty
 lib.bbg_poly_write.argtypes = [_vp, _sz, _vp, _sz]
 lib.bbg_stats_totals.argtypes = [_vp]
 lib.bbg_ntt_dist_fused_dev.argtypes = [_vp, _vp, _vp, _sz, _int, _sz, _vp, _int, _int, _vp]
+lib.bbg_ntt_dist_natural_dev.argtypes = [_vp, _vp, _vp, _vp, _sz, _int, _sz, _vp, _int, _int, _int, _vp]
 lib.bbg_peer_buffer_alloc.argtypes = [_sz, _vp, _vp]
 lib.bbg_peer_buffer_open.argtypes = [_vp, _vp]
 lib.bbg_peer_buffer_close.argtypes = [_vp]
@@ -529,6 +530,25 @@ def ntt_dist_fused_phase0(src, work, peer_ptrs, n, kind, rank, world, generator_
     tab = (ctypes.c_void_p * world)(*peer_ptrs)
     _check(lib.bbg_ntt_dist_fused_dev(src.data_ptr(), work.data_ptr(), ctypes.cast(tab, _vp), n, kind, generator_size,
                                       None if k is None else k.ctypes.data, rank, world, _stream_ptr(stream)))
+
+
+def ntt_dist_natural_phase(peer_in, work, peer_recv, peer_out, n, kind, rank, world, phase, generator_size=0, constant=None, stream=None):
+    """bbg_ntt_dist_natural_dev: natural blocks in and out over peer memory; the tables are lists of raw device pointers
+    (None where the phase does not use them), `work` a torch tensor or None"""
+    k = None if constant is None else _np(constant, 4)
+
+    def tab(ptrs):
+        return None if ptrs is None else ctypes.cast((ctypes.c_void_p * world)(*ptrs), _vp)
+    tabs = [tab(peer_in), tab(peer_recv), tab(peer_out)]
+    _check(lib.bbg_ntt_dist_natural_dev(tabs[0], None if work is None else work.data_ptr(), tabs[1], tabs[2], n, kind, generator_size,
+                                        None if k is None else k.ctypes.data, rank, world, phase, _stream_ptr(stream)))
+
+
+class RawCudaArray:
+    """a (rows, 4) int64 view of raw device memory for torch.as_tensor (the __cuda_array_interface__ protocol)"""
+
+    def __init__(self, ptr, rows):
+        self.__cuda_array_interface__ = {"shape": (rows, 4), "typestr": "<i8", "data": (int(ptr), False), "version": 3, "strides": None}
 
 
 def ntt_dist_phase_raw(src_ptr, dst, n, kind, rank, world, phase, generator_size=0, constant=None, stream=None):

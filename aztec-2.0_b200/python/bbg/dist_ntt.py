@@ -49,19 +49,23 @@ class FusedExchange:
     that a peer's stores for transform k + 1 never land in the buffer this rank is still reading for transform k),
     IPC handles exchanged once through torch.distributed."""
 
-    def __init__(self, bbg, n, rank, world, group=None):
+    def __init__(self, bbg, n, rank, world, group=None, natural=False):
         import torch
         import torch.distributed as dist
         self.bbg, self.n, self.rank, self.world, self.group = bbg, n, rank, world, group
         self.m = n // world
         self.own, self.peers = [], []
-        for _ in range(2):
+        # buffers 0, 1: receive buffers; natural: buffer 2 = this rank's natural input block, 3 = its natural output block
+        for _ in range(4 if natural else 2):
             ptr, handle = bbg.peer_buffer_alloc(self.m * 32)
             handles = [None] * world
             dist.all_gather_object(handles, handle, group=group)
             ptrs = [ptr if r == rank else bbg.peer_buffer_open(handles[r]) for r in range(world)]
             self.own.append(ptr)
             self.peers.append(ptrs)
+        if natural:
+            self.in_view = torch.as_tensor(bbg.RawCudaArray(self.own[2], self.m), device="cuda")
+            self.out_view = torch.as_tensor(bbg.RawCudaArray(self.own[3], self.m), device="cuda")
         self.turn = 0
         self.token = torch.zeros(1, dtype=torch.float32, device="cuda")
         dist.barrier(group=group)
@@ -71,12 +75,13 @@ class FusedExchange:
         import torch.distributed as dist
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
-        for b in range(2):
+        self.in_view = self.out_view = None
+        for b in range(len(self.own)):
             for r in range(self.world):
                 if r != self.rank:
                     self.bbg.peer_buffer_close(self.peers[b][r])
         dist.barrier(group=self.group)
-        for b in range(2):
+        for b in range(len(self.own)):
             self.bbg.peer_buffer_free(self.own[b])
 
 
@@ -95,6 +100,30 @@ def ntt_sharded_fused(bbg, local_in, n, kind, rank, world, xch, generator_size=0
     out = torch.empty_like(local_in)
     bbg.ntt_dist_phase_raw(xch.own[b], out, n, kind, rank, world, 1, generator_size, constant)
     return out
+
+
+def ntt_natural_fused(bbg, block_in, n, kind, rank, world, xch, generator_size=0, constant=None):
+    """SURVEY.md 8e contract -- natural contiguous block in, natural block out -- with NO all-to-all and no re-distribution:
+    every movement is peer-memory traffic issued by the NTT passes themselves (bbg_ntt_dist_natural_dev): the first pass
+    loads its sliced sub-array from the owners' input blocks, the pass before the transposition stores into the owners'
+    receive buffers, the last pass stores every output to the owner of its natural index.  Three one-word all-reduces order
+    the phases across ranks.  xch: FusedExchange(..., natural=True); block_in may be xch.in_view itself (no copy).  Returns
+    xch.out_view, valid until the next transform through the same exchange."""
+    import torch.distributed as dist
+    if block_in.data_ptr() != xch.in_view.data_ptr():
+        xch.in_view.copy_(block_in)
+    b = xch.turn
+    xch.turn ^= 1
+    work = xch.work if getattr(xch, "work", None) is not None else None
+    if work is None:
+        import torch
+        work = xch.work = torch.empty_like(xch.in_view)
+    dist.all_reduce(xch.token, group=xch.group)  # every rank's input block is in place
+    bbg.ntt_dist_natural_phase(xch.peers[2], work, xch.peers[b], None, n, kind, rank, world, 0, generator_size, constant)
+    dist.all_reduce(xch.token, group=xch.group)  # every rank's stores into the receive buffers are complete
+    bbg.ntt_dist_natural_phase(None, None, xch.peers[b], xch.peers[3], n, kind, rank, world, 1, generator_size, constant)
+    dist.all_reduce(xch.token, group=xch.group)  # every output block is complete
+    return xch.out_view
 
 
 def ntt_sharded_natural(bbg, block_in, n, kind, rank, world, generator_size=0, constant=None, group=None, phase_fn=None, layout=None):
@@ -132,11 +161,23 @@ def ntt_sharded_natural(bbg, block_in, n, kind, rank, world, generator_size=0, c
 def simulate(bbg, x, kind, world, generator_size=0, constant=None, fused=False):
     """All `world` ranks on one device. x: torch CUDA int64 (n, 4) natural order -> natural-order result.
     fused: the exchange is done by the pass before it storing into the "peers'" receive buffers (here: buffers of the
-    same device) -- the kernel and index maths of bbg_ntt_dist_fused_dev."""
+    same device) -- the kernel and index maths of bbg_ntt_dist_fused_dev.  fused = "natural": natural blocks in and out
+    through peer loads / stores as well (bbg_ntt_dist_natural_dev)."""
     import torch
     n = x.shape[0]
     in_pos, out_pos = bbg.ntt_dist_layout(n, world)
     m = n // world
+    if fused == "natural":
+        ins = [x[r * m:(r + 1) * m].contiguous() for r in range(world)]
+        recvs = [torch.zeros((m, 4), dtype=x.dtype, device=x.device) for _ in range(world)]
+        outs = [torch.zeros((m, 4), dtype=x.dtype, device=x.device) for _ in range(world)]
+        pin, prc, pout = ([t.data_ptr() for t in ts] for ts in (ins, recvs, outs))
+        for r in range(world):
+            bbg.ntt_dist_natural_phase(pin, torch.empty_like(ins[r]), prc, None, n, kind, r, world, 0, generator_size, constant)
+        for r in range(world):
+            bbg.ntt_dist_natural_phase(None, None, prc, pout, n, kind, r, world, 1, generator_size, constant)
+        torch.cuda.synchronize()
+        return torch.cat(outs, dim=0)
     if fused:
         recvs = [torch.zeros((m, 4), dtype=x.dtype, device=x.device) for _ in range(world)]
         ptrs = [t.data_ptr() for t in recvs]

@@ -915,7 +915,7 @@ def bench_ntt_sharded(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq
     fused = None
     if world <= 8:
         try:
-            xch = dist_ntt.FusedExchange(bbg, n, rank, world)
+            xch = dist_ntt.FusedExchange(bbg, n, rank, world, natural=True)
             fused = {}
             for name, kind in (("fft", bbg.FFT), ("ifft", bbg.IFFT), ("coset_fft", bbg.COSET_FFT)):
                 for _ in range(W):
@@ -933,6 +933,27 @@ def bench_ntt_sharded(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq
                     ms += a.elapsed_time(b)
                 barrier()
                 fused[name] = {"ms": max_over_ranks(ms) / K}
+            # natural contiguous blocks in and out: all-to-all re-distributions (3 NCCL all-to-alls) against peer
+            # loads / stores issued by the passes themselves (no collective but three one-word all-reduces)
+            natural = {}
+            for name, fn in (("nccl_3_all_to_alls", lambda: dist_ntt.ntt_sharded_natural(bbg, local, n, bbg.FFT, rank, world)),
+                             ("peer_memory", lambda: dist_ntt.ntt_natural_fused(bbg, xch.in_view, n, bbg.FFT, rank, world, xch))):
+                xch.in_view.copy_(local)
+                for _ in range(W):
+                    fn()
+                barrier()
+                ms = 0.0
+                for _ in range(K):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    flush.zero_()
+                    dist.barrier()
+                    a.record()
+                    fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    ms += a.elapsed_time(b)
+                barrier()
+                natural[name] = {"fft_ms": max_over_ranks(ms) / K}
         except Exception as e:  # IPC peer mapping unavailable on this box: the NCCL path above is the record
             fused = {"unavailable": str(e)[:200]}
             xch = None
@@ -945,10 +966,14 @@ def bench_ntt_sharded(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq
     for r in range(world):
         dist_ntt.insert_shard(full_in, gathered[r], in_pos, world, r)
     del gathered
-    ok = fused_ok = True
+    ok = fused_ok = natural_ok = True
+    m_blk = n // world
     for kind in (bbg.FFT, bbg.COSET_IFFT):
         full = full_in.clone()
         bbg.ntt(full, kind)
+        if fused is not None and "unavailable" not in fused:
+            got3 = dist_ntt.ntt_natural_fused(bbg, full_in[rank * m_blk:(rank + 1) * m_blk].contiguous(), n, kind, rank, world, xch)
+            natural_ok = natural_ok and bool(torch.equal(bbg.field_op_dev(1, 7, got3.clone()), bbg.field_op_dev(1, 7, full[rank * m_blk:(rank + 1) * m_blk].contiguous())))
         want = dist_ntt.extract_shard(full, out_pos, world, rank).contiguous()
         got = dist_ntt.ntt_sharded(bbg, local, n, kind, rank, world)
         ok = ok and bool(torch.equal(bbg.field_op_dev(1, 7, got), bbg.field_op_dev(1, 7, want)))
@@ -957,12 +982,14 @@ def bench_ntt_sharded(args, bbg, torch, dev, inputs, K, W, hbm_gbs, peak_src, fq
             fused_ok = fused_ok and bool(torch.equal(bbg.field_op_dev(1, 7, got2), bbg.field_op_dev(1, 7, want)))
             del got2
         del full, want, got
-    flag = torch.tensor([1 if ok else 0, 1 if fused_ok else 0], dtype=torch.int32, device=dev)
+    flag = torch.tensor([1 if ok else 0, 1 if fused_ok else 0, 1 if natural_ok else 0], dtype=torch.int32, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if fused is not None and "unavailable" not in fused:
         xch.close()
         fused = {"per_kind": fused, "ms_per_transform": statistics.mean(v["ms"] for v in fused.values()),
                  "parity": bool(flag[1].item() == 1),
+                 "natural_blocks": dict(natural, parity=bool(flag[2].item() == 1),
+                                        what="fft with natural contiguous blocks in and out (SURVEY 8e): three NCCL all-to-alls vs peer loads / stores by the passes"),
                  "how": "the pass before the exchange stores into the owners' receive buffers over NVLink peer memory (CUDA IPC); "
                         "a one-word all-reduce orders the last pass after every rank's stores"}
     mean_ms = statistics.mean(v["ms"] for v in per.values())

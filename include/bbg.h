@@ -194,6 +194,15 @@ int bbg_ntt_ex(void* coeffs, size_t n, int kind, size_t generator_size, const vo
  * all-reduce of one word is enough.  Alternate two receive buffers when transforms follow each other back to back. */
 int bbg_ntt_dist_fused_dev(const void* d_src, void* d_work, void* const* peer_recv, size_t n, int kind, size_t generator_size,
                            const void* constant, int rank, int world, void* stream);
+/* The multi-GPU transform on NATURAL contiguous blocks, the contract of SURVEY.md 8e: rank q holds x[q n / W, (q + 1) n / W)
+ * and ends with X[q n / W, (q + 1) n / W).  All movement is peer memory traffic issued by the passes themselves: phase 0
+ * loads its sub-array from the owners' input blocks (peer_in) in its first pass and stores into the owners' receive buffers
+ * (peer_recv) in its last; phase 1 transforms peer_recv[rank] and stores every output to the owner of its natural index
+ * (peer_out).  Every table holds `world` device pointers (<= 8) to buffers of n / world elements, entry `rank` being this
+ * rank's own; d_work: n / world elements of local scratch (phase 0).  The caller orders the phases across ranks with any
+ * stream-ordered barrier: all inputs written -> phase 0 everywhere -> phase 1 everywhere -> outputs readable. */
+int bbg_ntt_dist_natural_dev(void* const* peer_in, void* d_work, void* const* peer_recv, void* const* peer_out, size_t n, int kind,
+                             size_t generator_size, const void* constant, int rank, int world, int phase, void* stream);
 /* Peer-mapped device buffers (CUDA IPC, one process per GPU): alloc returns the pointer and a 64-byte handle to send to
  * the other ranks (any transport); open maps another rank's buffer into this process (lazy peer access over NVLink). */
 int bbg_peer_buffer_alloc(size_t bytes, void** d_ptr, void* ipc_handle64);

@@ -1,6 +1,7 @@
 """torchrun --nproc-per-node N scripts/dist_check.py : parity of the real multi-process paths (NCCL).
  * MSM sharded by point range + 96-byte partial all-gather + g1_sum  == oracle MSM over the whole range
  * four-step NTT with all_to_all_single                                  == the single-GPU transform of the same array
+ * natural contiguous blocks in and out with every movement a peer load / store of the NTT passes (bbg_ntt_dist_natural_dev)
  * the same with the exchange fused into the pass before it (peer stores over NVLink, CUDA IPC buffers), three
    transforms back to back per size so that both receive buffers of the double-buffering are used
 Prints one line per rank; exits non-zero on mismatch."""
@@ -45,7 +46,7 @@ def main():
         nn = 1 << lg
         x = inputs.fr_elements(88 + lg, nn, coarse_fraction=0.25)
         in_pos, out_pos = bbg.ntt_dist_layout(nn, world)
-        xch = dist_ntt.FusedExchange(bbg, nn, rank, world) if world <= 8 else None
+        xch = dist_ntt.FusedExchange(bbg, nn, rank, world, natural=True) if world <= 8 else None
         for kind, gs in ((bbg.FFT, 0), (bbg.COSET_FFT, nn // 4), (bbg.COSET_IFFT, 0)):
             shard = torch.from_numpy(np.ascontiguousarray(dist_ntt.extract_shard(x, in_pos, world, rank)).view(np.int64)).to(dev)
             out = dist_ntt.ntt_sharded(bbg, shard, nn, kind, rank, world, generator_size=gs).cpu().numpy().view(np.uint64)
@@ -59,6 +60,15 @@ def main():
                     if not fused_ok:
                         print("rank %d: fused exchange mismatch lg=%d kind=%d" % (rank, lg, kind), flush=True)
                     ok &= fused_ok
+                # natural blocks in / out, every movement a peer load or store of the passes themselves; twice in a row
+                mm = nn // world
+                block = torch.from_numpy(np.ascontiguousarray(x[rank * mm:(rank + 1) * mm]).view(np.int64)).to(dev)
+                for rep in range(2):
+                    o = dist_ntt.ntt_natural_fused(bbg, block, nn, kind, rank, world, xch, generator_size=gs).clone()
+                    nat_ok = bool(np.array_equal(orc.reduce(po.FR, o.cpu().numpy().view(np.uint64)), orc.reduce(po.FR, full[rank * mm:(rank + 1) * mm])))
+                    if not nat_ok:
+                        print("rank %d: natural-block transform mismatch lg=%d kind=%d rep=%d" % (rank, lg, kind, rep), flush=True)
+                    ok &= nat_ok
         if xch is not None:
             xch.close()
     print("rank %d/%d: %s" % (rank, world, "OK" if ok else "MISMATCH"), flush=True)

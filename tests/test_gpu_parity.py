@@ -468,6 +468,23 @@ def test_ntt_fused_exchange_simulated(bbg, orc, lg, world):
         assert np.array_equal(canon(orc, got), canon(orc, exp)), (lg, world, kind)
 
 
+@pytest.mark.parametrize("lg,world", [(12, 2), (14, 4), (16, 8), (17, 4), (20, 2), (22, 8)])
+def test_ntt_natural_blocks_over_peer_memory_simulated(bbg, orc, lg, world):
+    """bbg_ntt_dist_natural_dev: rank q holds the natural block x[q n / W, (q + 1) n / W) and ends with the natural block of
+    X; the first pass loads from the owners' blocks, the last pass stores to the owners' blocks (peer memory under torchrun,
+    buffers of one device here).  The concatenated output blocks must be the single-array transform."""
+    import torch
+    from bbg import dist_ntt
+    n = 1 << lg
+    x = inputs.fr_elements(3500 + lg, n, coarse_fraction=0.25)
+    const = inputs.fr_elements(3600 + lg, 1)[0]
+    xt = torch.from_numpy(x.view(np.int64)).cuda()
+    for kind, gs in ((bbg.FFT, 0), (bbg.COSET_FFT, n // 4), (bbg.COSET_IFFT, 0), (bbg.IFFT_WITH_CONSTANT, 0)):
+        got = dist_ntt.simulate(bbg, xt, kind, world, generator_size=gs, constant=const, fused="natural").cpu().numpy().view(np.uint64)
+        exp = bbg.ntt(x.copy(), kind, generator_size=gs, constant=const)
+        assert np.array_equal(canon(orc, got), canon(orc, exp)), (lg, world, kind)
+
+
 def test_multi_process_nccl_paths(bbg):
     """Real N > 1 run (torchrun, NCCL): needs >= 2 visible GPUs, skipped on a single-GPU box."""
     import subprocess
