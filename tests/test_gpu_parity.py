@@ -451,7 +451,7 @@ def test_ntt_multi_gpu_data_path_simulated(bbg, orc, lg, world):
         assert np.array_equal(canon(orc, exp), canon(orc, orc.ntt(po.NTT_IFFT_CONST, x, constant=const)))
 
 
-@pytest.mark.parametrize("lg,world", [(12, 2), (14, 4), (16, 8), (18, 8), (20, 2), (22, 4)])
+@pytest.mark.parametrize("lg,world", [(12, 2), (14, 4), (16, 8), (18, 8), (20, 2)])
 def test_ntt_fused_exchange_simulated(bbg, orc, lg, world):
     """bbg_ntt_dist_fused_dev: the pass before the exchange stores every element straight into the owner's receive
     buffer (NVLink peer memory in the torchrun path, buffers of the same device here) at the slot the all-to-all would
@@ -468,7 +468,7 @@ def test_ntt_fused_exchange_simulated(bbg, orc, lg, world):
         assert np.array_equal(canon(orc, got), canon(orc, exp)), (lg, world, kind)
 
 
-@pytest.mark.parametrize("lg,world", [(12, 2), (14, 4), (16, 8), (17, 4), (20, 2), (22, 8)])
+@pytest.mark.parametrize("lg,world", [(12, 2), (14, 4), (16, 8), (17, 4), (20, 8)])
 def test_ntt_natural_blocks_over_peer_memory_simulated(bbg, orc, lg, world):
     """bbg_ntt_dist_natural_dev: rank q holds the natural block x[q n / W, (q + 1) n / W) and ends with the natural block of
     X; the first pass loads from the owners' blocks, the last pass stores to the owners' blocks (peer memory under torchrun,
