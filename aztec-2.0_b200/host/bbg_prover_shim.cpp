@@ -255,19 +255,29 @@ extern "C" void bbg_shim_process_queue(waffle::work_queue* self)
         }
         case WorkType::IFFT: {
             // first work of a proof: the prover has just rewritten its wires and the Lagrange copies in wire_ffts
-            // (prover.cpp:184-186) behind any mirror kept from the previous proof
-            polynomial& wire = witness->wires.at(item.tag);
-            polynomial& wire_fft = key->wire_ffts.at(item.tag + "_fft");
-            check(bbg_resident_invalidate(&wire_fft[0], wire_fft.get_max_size() * sizeof(fr)));
-            // ... and the wire itself: its mirror was left AHEAD of host memory by the previous proof (coefficients kept on the
-            // device), so the library would trust it over the witness the prover has just written
-            check(bbg_resident_invalidate(&wire[0], wire.get_max_size() * sizeof(fr)));
-            // what polynomial::ifft does (polynomial.cpp:312-320), plus: the upload also seeds the mirror of the Lagrange
-            // copy in wire_fft[0, n), which round 3's grand product reads
-            if (n > wire.get_max_size()) wire.reserve(n);
-            check(bbg_wire_ifft(&wire[0], n, &wire_fft[0], defer ? BBG_KEEP_ON_DEVICE : 0));
-            wire.resize_unsafe(n);
-            ++i;
+            // (prover.cpp:184-186) behind any mirror kept from the previous proof.  All IFFT items in a row go down together.
+            std::vector<void*> cols;
+            std::vector<const void*> copies;
+            std::vector<polynomial*> polys;
+            size_t j = i;
+            while (j < items.size() && items[j].work_type == WorkType::IFFT && cols.size() < 16) {
+                polynomial& wire = witness->wires.at(items[j].tag);
+                polynomial& wire_fft = key->wire_ffts.at(items[j].tag + "_fft");
+                check(bbg_resident_invalidate(&wire_fft[0], wire_fft.get_max_size() * sizeof(fr)));
+                // ... and the wire itself: its mirror was left AHEAD of host memory by the previous proof (coefficients kept on
+                // the device), so the library would trust it over the witness the prover has just written
+                check(bbg_resident_invalidate(&wire[0], wire.get_max_size() * sizeof(fr)));
+                // what polynomial::ifft does (polynomial.cpp:312-320), plus: the upload also seeds the mirror of the Lagrange
+                // copy in wire_fft[0, n), which round 3's grand product reads
+                if (n > wire.get_max_size()) wire.reserve(n);
+                cols.push_back(&wire[0]);
+                copies.push_back(&wire_fft[0]);
+                polys.push_back(&wire);
+                ++j;
+            }
+            check(bbg_wire_ifft_batch(cols.data(), n, copies.data(), cols.size(), defer ? BBG_KEEP_ON_DEVICE : 0));
+            for (polynomial* w : polys) w->resize_unsafe(n);
+            i = j;
             break;
         }
         case WorkType::FFT: {

@@ -37,7 +37,7 @@ EXPORTS = [
     "bbg_pippenger_unsafe_batch", "bbg_pippenger_unsafe_batch_dev", "bbg_pippenger_batch",
     "bbg_field_op_dev", "bbg_g1_normalize", "bbg_resident_mode", "bbg_ntt_ex", "bbg_wire_coset_fft", "bbg_turbo_quotient",
     "bbg_permutation_quotient", "bbg_divide_by_pseudo_vanishing_polynomial", "bbg_compute_lagrange_polynomial_fft",
-    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_wire_ifft", "bbg_stats_totals", "bbg_ntt_dist_fused_dev", "bbg_ntt_dist_natural_dev",
+    "bbg_permutation_grand_product", "bbg_evaluate", "bbg_compute_opening_polynomial", "bbg_poly_write", "bbg_linear_combination", "bbg_evaluate_batch", "bbg_wire_ifft", "bbg_stats_totals", "bbg_ntt_dist_fused_dev", "bbg_ntt_dist_natural_dev", "bbg_wire_ifft_batch",
     "bbg_peer_buffer_alloc", "bbg_peer_buffer_open", "bbg_peer_buffer_close", "bbg_peer_buffer_free", "bbg_resident_invalidate", "bbg_resident_flush", "bbg_resident_stats",
 ]
 
@@ -125,6 +125,7 @@ lib.bbg_poly_write.argtypes = [_vp, _sz, _vp, _sz]
 lib.bbg_stats_totals.argtypes = [_vp]
 lib.bbg_ntt_dist_fused_dev.argtypes = [_vp, _vp, _vp, _sz, _int, _sz, _vp, _int, _int, _vp]
 lib.bbg_ntt_dist_natural_dev.argtypes = [_vp, _vp, _vp, _vp, _sz, _int, _sz, _vp, _int, _int, _int, _vp]
+lib.bbg_wire_ifft_batch.argtypes = [_vp, _sz, _vp, _sz, ctypes.c_uint]
 lib.bbg_peer_buffer_alloc.argtypes = [_sz, _vp, _vp]
 lib.bbg_peer_buffer_open.argtypes = [_vp, _vp]
 lib.bbg_peer_buffer_close.argtypes = [_vp]
@@ -678,6 +679,17 @@ def wire_coset_fft(wire, wire_fft, n, ext=4, flags=0):
 def wire_ifft(wire, lagrange_copy=None, flags=0):
     _check(lib.bbg_wire_ifft(wire.ctypes.data, wire.size // 4, None if lagrange_copy is None else lagrange_copy.ctypes.data, flags))
     return wire
+
+
+def wire_ifft_batch(wires, lagrange_copies=None, flags=0):
+    """bbg_wire_ifft_batch: in-place iffts of several equally long columns (numpy arrays)"""
+    k = len(wires)
+    w = (ctypes.c_void_p * k)(*[a.ctypes.data for a in wires])
+    lc = None
+    if lagrange_copies is not None:
+        lc = (ctypes.c_void_p * k)(*[None if a is None else a.ctypes.data for a in lagrange_copies])
+    _check(lib.bbg_wire_ifft_batch(ctypes.cast(w, _vp), wires[0].size // 4, None if lc is None else ctypes.cast(lc, _vp), k, flags))
+    return wires
 
 
 def poly_write(host_array, elem_offset, values):

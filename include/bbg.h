@@ -237,6 +237,10 @@ int bbg_wire_coset_fft(const void* wire, void* wire_fft, size_t n, size_t ext, u
  * uploaded for the transform instead of being uploaded again in round 3.  flags: 0 or BBG_KEEP_ON_DEVICE (the coefficients
  * stay in the wire's mirror: every later reader of a Turbo proof -- commitment, coset FFT, openings -- is a device step). */
 int bbg_wire_ifft(void* wire, size_t n, const void* lagrange_copy, unsigned flags);
+/* the IFFT items of one queue flush together (<= 16 columns of n elements; lagrange_copies or its entries may be null): every
+ * column is staged into pinned memory by the copy pool and uploaded asynchronously, so the staging of column k + 1 overlaps the
+ * upload and transform of column k; one synchronisation at the end */
+int bbg_wire_ifft_batch(void* const* wires, size_t n, const void* const* lagrange_copies, size_t count, unsigned flags);
 /* TransitionWidget::compute_quotient_contribution (bb/plonk/proof_system/widgets/transition_widgets/transition_widget.hpp:293-307)
  * for the TurboPLONK gate kernels: quotient[i] += identity(i) over the n_large-point coset domain.
  * polys: BBG_NUM_POLYNOMIALS pointers indexed like waffle::PolynomialIndex (types/polynomial_manifest.hpp:10-50) to the

@@ -257,3 +257,39 @@ def test_wire_ifft_seeds_the_lagrange_mirror(bbg, orc, ref):
     finally:
         bbg.resident_mode(False)
     assert np.array_equal(canon(orc, z), canon(orc, want_z))
+
+
+@pytest.mark.parametrize("resident,keep", [(False, False), (True, False), (True, True)])
+def test_wire_ifft_batch_matches_single_iffts(bbg, orc, ref, resident, keep):
+    """bbg_wire_ifft_batch (the IFFT items of one queue flush: columns staged into pinned memory by the copy pool, uploaded
+    asynchronously, one synchronisation): every column must be the reference's ifft, the Lagrange copies' mirrors must be
+    seeded, and with BBG_KEEP_ON_DEVICE the coefficients must be readable by the next device step (a commitment-style
+    evaluate) and come home on bbg_resident_flush."""
+    n = 1 << 12
+    lag = [inputs.fr_elements(1800 + k, n) for k in range(5)]
+    want = [ref.ntt(po.NTT_IFFT, x) for x in lag]
+    zeta = inputs.fr_elements(1810, 1)[0]
+    bbg.resident_mode(resident)
+    try:
+        wires = [w.copy() for w in lag]
+        copies = [np.zeros((4 * n + 4, 4), dtype=np.uint64) for _ in range(5)]
+        for k in range(5):
+            copies[k][:n] = wires[k]
+        copies[4] = None  # an item without a Lagrange copy
+        bbg.wire_ifft_batch(wires, copies, bbg.KEEP_ON_DEVICE if keep else 0)
+        if keep:
+            for k in range(5):
+                assert np.array_equal(canon(orc, bbg.evaluate(wires[k], zeta)), canon(orc, ref.evaluate(want[k], zeta))), k
+                bbg.resident_flush(wires[k])
+        for k in range(5):
+            assert np.array_equal(canon(orc, wires[k]), canon(orc, want[k])), k
+        if resident:
+            s0 = bbg.resident_stats()
+            sigmas = [inputs.fr_elements(1820 + k, n) for k in range(4)]
+            beta, gamma = inputs.fr_elements(1830, 1)[0], inputs.fr_elements(1831, 1)[0]
+            z = bbg.permutation_grand_product([c[:n] for c in copies[:4]], sigmas, n, beta, gamma)
+            assert bbg.resident_stats()["hits"] >= s0["hits"] + 4
+            bbg.resident_mode(False)
+            assert np.array_equal(canon(orc, z), canon(orc, bbg.permutation_grand_product(lag[:4], sigmas, n, beta, gamma)))
+    finally:
+        bbg.resident_mode(False)
