@@ -27,9 +27,10 @@ def main(lib, out):
     total = collections.Counter()
     with open(out, "w") as f:
         f.write("# SASS opcode histogram per kernel (`cuobjdump -sass %s`, sm_100a)\n\n" % lib)
-        f.write("Static instruction counts (not execution counts). IMAD.WIDE is the half-rate 32x32->64 multiply-add the 254-bit Montgomery\n"
-                "product is made of; UTMALDG / UBLKCP / LDGSTS (TMA / bulk / async copies) and HMMA / UTCMMA (tensor cores) do not occur:\n"
-                "this is carry-propagating integer work on the fmaheavy pipe (DESIGN.md 3).\n\n")
+        f.write("Static instruction counts (not execution counts). IMAD.WIDE is the quarter-rate 32x32->64 multiply-add the 254-bit Montgomery\n"
+                "product is made of: this is carry-propagating integer work on the fmaheavy pipe (DESIGN.md 3).  HMMA / UTCMMA (tensor cores)\n"
+                "do not occur.  UBLKCP (cp.async.bulk, the TMA bulk copy that stages the stage twiddles of the E = 4 NTT pass into shared\n"
+                "memory) and LDGSTS (cp.async, the persistent-pass experiment) occur only in `k_ntt_pass`; the totals are in the last line.\n\n")
         f.write("| kernel | instructions | IMAD.WIDE | IMAD | IADD3 | LOP3+SEL | SHFL | LDG/STG | LDS/STS | LDL/STL | BAR | other top |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|\n")
         for (name, c), dm in zip(kernels.items(), demangle):
             n = sum(c.values())
