@@ -108,6 +108,106 @@ def gen_mul(p, sqr=False):
     return pr
 
 
+def gen_sqr(p):
+    """r = a*a*R^-1 (coarse), the same integer (a*a + m*p) / 2^256 as gen_mul(p, sqr=True), with 100 instead of 128 wide
+    multiply-adds: the off-diagonal products a_i*a_j (i < j) are formed once, doubled with funnel shifts, and the diagonal
+    squares ride in on the wide multiply-adds that add them; the 512-bit square's low half is then reduced with the same
+    two-accumulator steps as gen_mul and the high half is added at the end ((T_lo + m p) / R + T_hi).
+
+    Phase A keeps TWO arrays of aligned 64-bit lanes, one for even and one for odd limb positions (products a_i*a_j land at
+    position i + j).  Row j (multiplier a_j, i > j) is one carry chain per array over consecutive lanes; its carry-out
+    lands in the low limb of the next lane of the same array, which at that moment holds at most earlier carries (rows are
+    taken in order and their top lanes never decrease), so one addc ends the chain."""
+    pl = limbs(p)
+    ninv = (-pow(p, -1, 1 << 32)) & MASK
+    pr = Prog()
+    A = ["a%d" % i for i in range(N)]
+    lo, hi = {}, {}  # lane at limb position pos -> registers of limbs pos, pos + 1 (missing = zero)
+
+    def reg(d, pos):
+        if d.get(pos) is None:
+            d[pos] = pr.tmp()
+            return d[pos], 0
+        return d[pos], d[pos]
+
+    for j in range(N - 1):
+        for par in (1, 0):  # the chain of odd-position lanes, then the even one (they are independent numbers)
+            idxs = [i for i in range(j + 1, N) if (i + j) % 2 == par]
+            if not idxs:
+                continue
+            for n_, i in enumerate(idxs):
+                pos = i + j
+                dl, cl = reg(lo, pos)
+                dh, ch = reg(hi, pos)
+                pr.emit("mad.lo.cc" if n_ == 0 else "madc.lo.cc", dl, A[i], A[j], cl)
+                pr.emit("madc.hi.cc", dh, A[i], A[j], ch)
+            top = idxs[-1] + j + 2
+            dl, cl = reg(lo, top)
+            pr.emit("addc", dl, cl, 0)
+    # U = E + (O << 32): limb k gets the low limb of lane k and the high limb of lane k - 1 (one of each array)
+    u = [None] * (2 * N)
+    first = True
+    for k in range(1, 2 * N):
+        x = lo.get(k)
+        y = hi.get(k - 1)
+        if x is None and y is None:
+            # nothing lands here (only possible above the top carry): keep the chain's carry
+            u[k] = pr.tmp()
+            pr.emit("add.cc" if first else ("addc.cc" if k != 2 * N - 1 else "addc"), u[k], 0, 0)
+        else:
+            u[k] = pr.tmp()
+            pr.emit("add.cc" if first else ("addc.cc" if k != 2 * N - 1 else "addc"), u[k], x if x is not None else 0, y if y is not None else 0)
+        first = False
+    # T = 2 U + sum_i a_i^2 2^(64 i): the doubling is a funnel shift per limb, the squares come in on wide multiply-adds
+    t = [None] * (2 * N)
+    for k in range(1, 2 * N):
+        t[k] = pr.tmp()
+        if k == 1:
+            pr.emit("add", t[k], u[k], u[k])
+        else:
+            pr.emit("shf", t[k], u[k - 1], u[k], 1)
+    T = [pr.tmp() for _ in range(2 * N)]
+    for i in range(N):
+        pr.emit("mad.lo.cc" if i == 0 else "madc.lo.cc", T[2 * i], A[i], A[i], t[2 * i] if t[2 * i] is not None else 0)
+        pr.emit("madc.hi.cc" if i != N - 1 else "madc.hi", T[2 * i + 1], A[i], A[i], t[2 * i + 1])
+    # Montgomery-reduce the low half with gen_mul's steps (no product rows)
+    P = T[:N]
+    Q = [None] * N
+    L = None
+    for j in range(N):
+        carry = False
+        if j > 0:
+            pr.emit("add.cc", P[0], P[0], L)
+            carry = True
+        m = pr.tmp()
+        pr.emit("mul.lo", m, P[0], ninv)
+        for n_, i in enumerate(range(1, N, 2)):
+            lo_c = Q[i - 1] if Q[i - 1] is not None else 0
+            hi_c = Q[i] if Q[i] is not None else 0
+            if Q[i - 1] is None:
+                Q[i - 1] = pr.tmp()
+            if Q[i] is None:
+                Q[i] = pr.tmp()
+            pr.emit("madc.lo.cc" if (carry or n_ > 0) else "mad.lo.cc", Q[i - 1], m, pl[i], lo_c)
+            pr.emit("madc.hi.cc" if i != N - 1 else "madc.hi", Q[i], m, pl[i], hi_c)
+        for i in range(0, N, 2):
+            pr.emit("mad.lo.cc" if i == 0 else "madc.lo.cc", P[i], m, pl[i], P[i])
+            pr.emit("madc.hi.cc", P[i + 1], m, pl[i], P[i + 1])
+        pr.emit("addc", Q[N - 1], Q[N - 1], 0)
+        L = P[1]
+        P, Q = Q, P[2:] + [None, None]
+    # (T_lo + m p) / R = P + (Q shifted, stray limb at 0); then + T_hi
+    S = [pr.tmp() for _ in range(N)]
+    pr.emit("add.cc", S[0], P[0], L)
+    for k in range(1, N):
+        q = Q[k - 1]
+        pr.emit("addc.cc" if k != N - 1 else "addc", S[k], P[k], q if q is not None else 0)
+    R = ["r%d" % i for i in range(N)]
+    for k in range(N):
+        pr.emit("add.cc" if k == 0 else ("addc.cc" if k != N - 1 else "addc"), R[k], S[k], T[N + k])
+    return pr
+
+
 def emulate(pr, env):
     """Run the IR with PTX carry-flag semantics. env: dict reg -> value."""
     cc = 0
@@ -133,6 +233,9 @@ def emulate(pr, env):
             env[dst] = s & MASK
             if op.endswith(".cc"):
                 cc = s >> 32
+        elif name == "shf":
+            # shf.l.wrap.b32 d, lo, hi, n: the upper word of (hi:lo) << n
+            env[dst] = ((val(b) << val(c)) | (val(a) >> (32 - val(c)))) & MASK
         else:
             raise ValueError(op)
         assert cc in (0, 1)
@@ -145,10 +248,12 @@ def selftest():
         p = f["p"]
         rinv = pow(1 << 256, -1, p)
         for sqr in (False, True):
-            pr = gen_mul(p, sqr)
-            for trial in range(3000):
+          for pr, label in ((gen_mul(p, sqr), "sqr" if sqr else "mul"),) + (((gen_sqr(p), "sqr (dedicated, --dedicated-sqr)"),) if sqr else ()):
+            for trial in range(6000 if sqr else 3000):
                 hi = 2 * p
-                a = random.choice([0, 1, p - 1, p, p + 1, 2 * p - 1, random.randrange(hi), random.randrange(hi)])
+                a = random.choice([0, 1, p - 1, p, p + 1, 2 * p - 1, random.randrange(hi), random.randrange(hi), random.randrange(hi),
+                                   (2 * p - 1 - random.randrange(1 << 40)), random.randrange(1 << random.randrange(1, 255)),
+                                   sum(random.choice([0, MASK, 0x80000000, 1]) << (32 * i) for i in range(N)) % hi])
                 b = a if sqr else random.choice([0, 1, p - 1, p, 2 * p - 1, random.randrange(hi), random.randrange(hi)])
                 env = {}
                 for i, v in enumerate(limbs(a)):
@@ -162,7 +267,9 @@ def selftest():
                 assert r == exact, (fname, sqr, hex(a), hex(b), hex(r), hex(exact))
                 assert r < 2 * p and r % p == (a * b * rinv) % p
             nmad = sum(1 for i in pr.ins if i[0].startswith(("mad", "mul")))
-            print("%s %s: ok  (%d instructions, %d mul/mad)" % (fname, "sqr" if sqr else "mul", len(pr.ins), nmad))
+            nwide = sum(1 for i in pr.ins if i[0].startswith(("mad.hi", "madc.hi", "mul.hi")))
+            print("%s %s: ok  (%d instructions, %d mul/mad = %d wide pairs + %d single)" % (
+                fname, label, len(pr.ins), nmad, nwide, nmad - 2 * nwide))
 
 
 def to_ptx(pr, fname, opname, sqr):
@@ -189,6 +296,8 @@ def to_ptx(pr, fname, opname, sqr):
             lines.append("%s.u32 %s, %s, %s;" % (op, o(dst), o(a), o(b)))
         elif name in ("mad", "madc"):
             lines.append("%s.u32 %s, %s, %s, %s;" % (op, o(dst), o(a), o(b), o(c)))
+        elif name == "shf":
+            lines.append("shf.l.wrap.b32 %s, %s, %s, %d;" % (o(dst), o(a), o(b), c))
         else:
             lines.append("%s.u32 %s, %s, %s;" % (op, o(dst), o(a), o(b)))
     body = "\n".join('        "%s\\n\\t"' % ln for ln in lines)
@@ -212,7 +321,12 @@ def main():
            "#pragma once", "#include <cstdint>", ""]
     for fname, f in FIELDS.items():
         out.append(to_ptx(gen_mul(f["p"], False), fname, "mul", False))
-        out.append(to_ptx(gen_mul(f["p"], True), fname, "sqr", True))
+        # The dedicated squaring (gen_sqr: 100 instead of 128 wide multiply-adds, bit-identical results, the whole GPU suite
+        # passes with it) is NOT what ships: measured on B200 the MSM's accumulate kernel went from 2.14 to 2.18 ms with it --
+        # 7 % fewer IMAD.WIDE, but +110 IADD3 / +75 SHF per kernel and 34 instead of 12 spilled bytes at the 128-register cap
+        # cost more than the multiplier slots they free.  `--dedicated-sqr` emits it for experiments.
+        dedicated = "--dedicated-sqr" in sys.argv
+        out.append(to_ptx(gen_sqr(f["p"]) if dedicated else gen_mul(f["p"], True), fname, "sqr", True))
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mont_asm.inc")
     with open(path, "w") as fh:
         fh.write("\n".join(out))
