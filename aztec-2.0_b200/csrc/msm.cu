@@ -288,6 +288,8 @@ __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* __restrict__
 
 // DIRECT: the entry at position pos IS points[pos] (the output of the pairwise passes); otherwise it is the schedule
 // word sorted[pos] = (table index << 1) | negate.
+// Launch bounds (128, 4): 128 registers with 12 spilled bytes and 16 warps per SM.  (128, 3) gives 148 registers, no spills
+// and 12 warps: measured slower, 2.142 -> 2.177 ms at 2^20 (profiles/r2_msm_acc_ctas_ab.txt).
 template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS, 4) k_msm_accumulate(const uint32_t* __restrict__ sorted,
                                                                    const uint32_t* __restrict__ offsets, // G+1
