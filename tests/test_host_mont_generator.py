@@ -13,7 +13,9 @@ CSRC = os.path.join(ROOT, "aztec-2.0_b200", "csrc")
 
 def test_generator_selftest():
     out = subprocess.run([sys.executable, os.path.join(CSRC, "gen_mont.py"), "--selftest"], capture_output=True, text=True, check=True).stdout
-    for key in ("fq mul: ok", "fq sqr: ok", "fr mul: ok", "fr sqr: ok"):
+    for key in ("fq mul: ok", "fq sqr: ok", "fr mul: ok", "fr sqr: ok",
+                # the dedicated squaring kept behind --dedicated-sqr (100 wide multiply-adds) must stay exact as well
+                "fq sqr (dedicated, --dedicated-sqr): ok", "fr sqr (dedicated, --dedicated-sqr): ok", "100 wide pairs"):
         assert key in out, out
 
 
